@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- observations/sec per Levenberg-Marquardt iteration (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one LM iteration of the hot path = compute_update(lambda) + compute_cost of the
+candidate (linearise + eliminate -> [all-reduce] -> reduced solve -> back-substitute + retract +
+candidate cost), the accept path of bundle_adjuster.py:127-157.
+
+Workload: BASELINE config 2 (200 cameras / 50,000 points / 500,000 observations, sigma = 1 px)
+per GPU.  With N > 1 ranks the scene has N x 50,000 points over the same 200 cameras (weak
+scaling), points sharded contiguously, the reduced camera system all-reduced over NCCL once
+per step plus an 16-byte cost reduction.
+
+Keys of the JSON line: see the builder contract.  `value` = device-timed throughput with the
+scene resident in HBM; `e2e` = the same iteration driven from HOST buffers (pinned), H2D of
+the whole scene + D2H of the update and costs inside the timed region; `roofline` = the
+dominant kernel (linearize_eliminate) against the measured HBM peak; `cpu_baseline` = the CPU
+oracle (numpy restatement of the reference, oracle/ba_oracle.py) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CAMS, PTS_PER_GPU, K_OBS, SEED = 200, 50_000, 10, 1
+DAMPING = 10.0     # init_damping of BundleAdjuster.optimize (bundle_adjuster.py:120)
+HBM_FALLBACK_GBS = 6650.0
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def scene_arrays(n_ranks):
+    from pysfm_b200 import synthetic
+    return synthetic.make_arrays(CAMS, PTS_PER_GPU * n_ranks, K_OBS, SEED)
+
+
+def oracle_problem(a):
+    from oracle import ba_oracle
+    nc, nt = len(a["Rs"]), len(a["pts"])
+    return ba_oracle.Problem(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"],
+                             ('gaussian', np.eye(2)), np.arange(1, nc), np.arange(nt))
+
+
+def subsample_points(a, frac):
+    """Keep the first frac of the points (all cameras) -- a bounded sample of the workload."""
+    nt = max(1, int(len(a["pts"]) * frac))
+    keep = a["obs_track"] < nt
+    b = dict(a)
+    b["pts"] = a["pts"][:nt]
+    for k in ("obs_cam", "obs_track", "obs_uv"):
+        b[k] = a[k][keep]
+    return b
+
+
+def time_oracle(a, steps, warmup, budget_s):
+    """Times oracle.lm_iteration; shrinks the sample so (steps+warmup) iterations fit budget_s."""
+    from oracle import ba_oracle
+    frac = 1.0
+    P = oracle_problem(a)
+    t0 = time.perf_counter()
+    c0 = time.process_time()
+    ba_oracle.lm_iteration(P, DAMPING)
+    first = time.perf_counter() - t0
+    cores_eff = max(1, int(round((time.process_time() - c0) / max(first, 1e-9))))
+    done_warm = 1
+    if first * (steps + warmup - 1) > budget_s:
+        frac = max(0.02, budget_s / (first * (steps + warmup)))
+        P = oracle_problem(subsample_points(a, frac))
+        done_warm = 0
+    for _ in range(max(0, warmup - done_warm)):
+        ba_oracle.lm_iteration(P, DAMPING)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ba_oracle.lm_iteration(P, DAMPING)
+        times.append(time.perf_counter() - t0)
+    n_obs = len(P.obs_cam)
+    t = float(np.sum(times))
+    sample = "%d cams / %d pts / %d obs (%.0f%% of the workload's points), %d timed LM iterations of oracle/ba_oracle.py" % (
+        P.nc, P.nt, n_obs, 100 * frac, steps)
+    return n_obs * steps / t, 1e3 * t / steps, cores_eff, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a = scene_arrays(args.gpus)
+    val, ms, cores, sample = time_oracle(a, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "observations/sec per LM iteration", "value": val, "unit": "obs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(),
+                         "note": "numpy/scipy restatement of pysfm's BundleAdjuster pinned to the unmodified reference "
+                                 "(tests/golden); the verbatim py2 reference cannot run on the GPU box and would need "
+                                 "~2.9 h per iteration at this size (BASELINE.md)"},
+        "e2e": {"value": val, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n):
+    return {"workload": "BASELINE config 2 per GPU: %d cameras / %d points / %d observations (k=%d per point), "
+                        "pixel noise sigma=1.0, GaussianModel(1.), camera 0 fixed, damping=%g" % (
+                            CAMS, PTS_PER_GPU * n, PTS_PER_GPU * n * K_OBS, K_OBS, DAMPING),
+            "cameras": CAMS, "points": PTS_PER_GPU * n, "observations": PTS_PER_GPU * n * K_OBS,
+            "parallelism": "points sharded over %d rank(s); reduced camera system all-reduced (NCCL)" % n if n > 1
+            else "single GPU",
+            "l2": "L2 flushed (256 MiB write) before every timed step"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pysfm_b200 import _lib
+    from pysfm_b200.bundle import Bundle
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
+
+    a = scene_arrays(world)
+    bundle = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"])
+    ba = BundleAdjuster(device=dev, verbose=False, shard=(world > 1))
+    ba.set_bundle(bundle)
+    prob = ba._problem
+    sc = prob.scene
+    n_obs_total = len(a["obs_cam"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        prob.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
+        ba._allreduce_system()
+        prob.solve(None)
+        prob.backsub_retract_cost()
+        ba._allreduce_costs()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = prob.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        for s in range(args.steps):
+            flush.zero_()
+            ev[s][0].record()
+            step()
+            ev[s][1].record()
+        barrier()
+    launches = prob.launch_count() - launches0
+    total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ev))
+    cost, cand_cost, status = prob.read_scalars()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = n_obs_total * args.steps / (total_ms * 1e-3)
+
+    # ---- per-stage device times (same stream, CUDA events), L2 flushed before each step ------
+    stage_names = ["linearize_eliminate", "allreduce_system", "solve", "backsub_retract_cost"]
+    stage_ms = dict((k, 0.0) for k in stage_names)
+    reps = min(args.steps, 10)
+    for _ in range(reps):
+        flush.zero_()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        marks[0].record()
+        prob.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
+        marks[1].record()
+        ba._allreduce_system()
+        marks[2].record()
+        prob.solve(None)
+        marks[3].record()
+        prob.backsub_retract_cost()
+        ba._allreduce_costs()
+        marks[4].record()
+        torch.cuda.synchronize(dev)
+        for i, k in enumerate(stage_names):
+            stage_ms[k] += marks[i].elapsed_time(marks[i + 1]) / reps
+
+    # ---- end to end from host buffers -------------------------------------------------------
+    pin = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt).pin_memory()
+    h = dict(pt_ptr=pin(sc.pt_ptr, torch.int32), obs_cam=pin(sc.obs_cam, torch.int32),
+             obs_uv=pin(sc.obs_uv, torch.float64), R=pin(sc.cam_R, torch.float64),
+             t=pin(sc.cam_t, torch.float64), x=pin(sc.pts, torch.float64))
+    out_dC = torch.empty(prob.n_sys, dtype=torch.float64).pin_memory()
+    out_dP = torch.empty(sc.n_pt * 3, dtype=torch.float64).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in h.values())
+    d2h = (out_dC.numel() + out_dP.numel() + 4) * 8
+
+    def e2e_step():
+        prob.pt_ptr.copy_(h["pt_ptr"], non_blocking=True)
+        prob.obs_cam.copy_(h["obs_cam"], non_blocking=True)
+        prob.obs_uv.copy_(h["obs_uv"], non_blocking=True)
+        prob.upload_state(h["R"], h["t"], h["x"], non_blocking=True)
+        _, _, st = ba._trial(DAMPING)          # linearise .. candidate cost, reads cost/cand_cost/status
+        assert st == 0
+        prob.copy_solution_to(out_dC, out_dP)   # D2H of the camera and point updates
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = n_obs_total * args.steps / float(t.item())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        n = prob.n_sys
+        n_pt_local, n_obs_local = sc.n_pt, sc.n_obs
+        # algorithmic bytes of ONE linearize_eliminate launch:
+        #   20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + S triangle + rhs written once + cameras
+        elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * sc.n_cam
+        elim_s = stage_ms["linearize_eliminate"] * 1e-3
+        achieved = elim_bytes / elim_s / 1e9
+        iter_bytes = 40 * n_obs_local + 224 * n_pt_local + 16 * n * n + 288 * sc.n_cam
+        pairs = float(np.sum((np.diff(sc.pt_ptr).astype(np.float64)) * (np.diff(sc.pt_ptr) + 1) / 2))
+        flops_iter = 300.0 * n_obs_local + 216.0 * pairs + n ** 3 / 3.0
+        line = {
+            "metric": "observations/sec per LM iteration", "value": value, "unit": "obs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_val, "unit": "obs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * float(t.item()) / args.steps,
+                    "path": "pinned host scene -> H2D -> BundleAdjuster._trial (C ABI) -> D2H of dC, dP, costs"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "linearize_eliminate_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": int(elim_bytes), "kernel_ms": stage_ms["linearize_eliminate"]},
+            "iteration_roofline": {"algorithmic_bytes": int(iter_bytes), "achieved_GBs": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+                                   "fp64_flops": flops_iter, "fp64_tflops": flops_iter / (total_ms / args.steps * 1e-3) / 1e12},
+            "stages_ms": stage_ms,
+            "final": {"cost": cost, "cand_cost": cand_cost, "solve_status": status},
+        }
+        if world == 1:
+            val, ms, cores, sample = time_oracle(a, steps=2, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {"value": val, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "ms_per_step": ms, "host_cpus": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

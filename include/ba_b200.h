@@ -1,0 +1,164 @@
+/*
+ * ba_b200.h -- C ABI of the B200-native bundle-adjustment inner loop (libba_b200.so).
+ *
+ * The reference (alexflint/pysfm) has no FFI: its boundary for this path is the Python
+ * class bundle_adjuster.BundleAdjuster.  Each entry point below replaces one stage of that
+ * class and cites the reference code it stands in for (paths relative to the pysfm tree).
+ * The Python drop-in (pysfm_b200/bundle_adjuster.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a pysfm maintainer would add.
+ *
+ * Conventions
+ *   - every entry returns an int status (BA_OK, ...); nothing throws across the boundary;
+ *   - plain pointers and sizes only, no torch/C++ types;
+ *   - "dev" pointers are CUDA device pointers owned by the CALLER (the Python side holds them
+ *     in torch tensors); the library owns only the opaque handle and its internal workspace;
+ *   - all kernels are enqueued on the caller's stream (cudaStream_t passed as void*), nothing
+ *     synchronises except ba_read_scalars / ba_get_* / ba_sync;
+ *   - one handle per GPU (rank); handles are not thread-safe; there is no global state;
+ *   - all arithmetic is IEEE FP64, indices are int32.
+ *
+ * Data layout in HBM (SoA: one array per attribute, never an array of camera/track objects)
+ *   cam_R   [n_cam][9]   row-major rotation            cam_t [n_cam][3]
+ *   pts     [n_pt][3]
+ *   pt_ptr  [n_pt+1]     CSR offsets into the observation arrays (observations are
+ *                        point-major; inside one point they are sorted by camera slot)
+ *   obs_cam [n_obs]      camera position (0..n_cam-1) of each observation
+ *   obs_uv  [n_obs][2]   measured pixel
+ *   cam_slot[n_cam]      position of the camera in the reduced system (0..n_opt_cam-1),
+ *                        or -1 when the camera is held fixed
+ *   pt_slot [n_pt]       position of the point in the structure update, or -1 when the
+ *                        track is eliminated but not updated (track_mask semantics)
+ *   sys     [ld*ld + ld] reduced camera system: S stored with leading dimension
+ *                        ld = ba_system_ld(6*n_opt_cam); only the triangle {row<=col} in
+ *                        row-major terms is accumulated (== column-major lower), followed by
+ *                        the right-hand side b.  This is the one buffer that is all-reduced
+ *                        across ranks when points are sharded.
+ */
+#ifndef BA_B200_H_
+#define BA_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ba_context* ba_handle;
+
+enum {
+  BA_OK = 0,
+  BA_ERR_ILLCONDITIONED = 1, /* reduced system not positive definite -> Python raises
+                                NormalEquationsIllconditioned (bundle_adjuster.py:27,302-305) */
+  BA_ERR_CUDA = 2,
+  BA_ERR_NCCL = 3,           /* reserved: collectives are issued by the host side */
+  BA_ERR_BAD_ARGUMENT = 4,
+  BA_ERR_NOT_BOUND = 5
+};
+
+enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */
+
+/* flags for ba_linearize_eliminate */
+enum {
+  BA_WANT_BLOCKS = 1, /* also emit HCCs/HPPs/HCPs/bCs/bPs (prepare_schur_complement outputs) */
+  BA_WANT_SCHUR = 2   /* damp, invert point blocks, accumulate S and b */
+};
+
+/* selectors for ba_get_array */
+enum {
+  BA_ARR_HCC = 0,   /* [n_cam][6][6]   bundle_adjuster.py:106 */
+  BA_ARR_HPP = 1,   /* [n_pt][3][3]    :108 */
+  BA_ARR_HCP = 2,   /* [n_obs][6][3]   :107, sparse: one block per observation */
+  BA_ARR_BC = 3,    /* [n_cam][6]      :110 */
+  BA_ARR_BP = 4,    /* [n_pt][3]       :111 */
+  BA_ARR_HPP_INV = 5, /* [n_pt][3][3]  :109 */
+  BA_ARR_DC = 6,    /* [n_opt_cam][6]  solution of the reduced system (before negation) */
+  BA_ARR_DP = 7,    /* [n_pt][3]       back-substituted point update (before negation); rows of
+                                       tracks that are eliminated but not updated are zero */
+  BA_ARR_RESIDUAL = 8, /* [n_obs][2]   bundle.py:251 (ba_eval_observations) */
+  BA_ARR_JC = 9,    /* [n_obs][2][6]   bundle.py:255-277 */
+  BA_ARR_JP = 10    /* [n_obs][2][3] */
+};
+
+const char* ba_version(void);
+const char* ba_last_error(ba_handle h); /* text of the last CUDA error seen by this handle */
+
+/* Leading dimension used for an n x n reduced system (n padded up to the solver tile). */
+int ba_system_ld(int n);
+
+/* Problem sizes are fixed per handle (set_bundle, bundle_adjuster.py:54-114). */
+int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_opt_pt,
+              ba_handle* out);
+int ba_destroy(ba_handle h);
+
+/* K (bundle.py:138) and the sensor model (sensor_model.py) -- HOST pointers, copied.
+ * params: Gaussian -> row-major 2x2 L; Cauchy -> {sigma, sigma^2, linear_window, 0}. */
+int ba_set_intrinsics(ba_handle h, const double* K9_host);
+int ba_set_sensor_model(ba_handle h, int kind, const double* params4_host);
+
+/* Visibility structure (Track.measurements, bundle.py:95-111), constant across iterations. */
+int ba_bind_structure(ba_handle h, const int* pt_ptr_dev, const int* obs_cam_dev,
+                      const double* obs_uv_dev, const int* cam_slot_dev, const int* pt_slot_dev);
+/* Current estimate and the candidate ("bnext", bundle_adjuster.py:143) parameter buffers. */
+int ba_bind_state(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts_dev);
+int ba_bind_candidate(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts_dev);
+/* Reduced system buffer [ld*ld + ld] doubles, see layout above. */
+int ba_bind_system(ba_handle h, double* sys_dev);
+
+/* prepare_schur_complement + apply_damping + compute_schur_complement in one pass over the
+ * observations (bundle_adjuster.py:211-234, :238-242, :247-278).  Zeroes and accumulates the
+ * bound system buffer; also leaves the current cost (compute_cost, :165-171) in the scalars.
+ * pinv_rcond < 0 selects the plain inverse (SCHUR_COMPLIMENT_PINV_THRESHOLD = None, :253). */
+int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int flags,
+                           void* stream);
+
+/* solve_motion_normal_eqns (bundle_adjuster.py:281-312): mirrors nothing, factors the
+ * accumulated triangle in place (Cholesky) and solves for dC.  cam_param_mask_host is NULL or
+ * 6*n_opt_cam bytes (0 = parameter frozen, :296-309).  A non-positive pivot is recorded in
+ * the scalars and reported by ba_read_scalars as BA_ERR_ILLCONDITIONED. */
+int ba_solve(ba_handle h, const unsigned char* cam_param_mask_host, void* stream);
+
+/* backsubstitute (:316-331) + update_motion/update_structure on the candidate (:334-343,
+ * bundle.py:76-80: R <- R exp(-dC[:3]), t <- t - dC[3:], x <- x - dP) + compute_cost of the
+ * candidate (:146). */
+int ba_backsub_retract_cost(ba_handle h, void* stream);
+
+/* compute_cost(bundle) (:165-171) of the CURRENT state only; result in the scalars. */
+int ba_cost(ba_handle h, void* stream);
+
+/* Accept the candidate (bundle_adjuster.py:151): swaps the state/candidate bindings. */
+int ba_accept(ba_handle h);
+
+/* Blocks until the stream is idle, then returns cost, candidate cost and the solver status
+ * (BA_OK or BA_ERR_ILLCONDITIONED).  The only synchronising call on the product path. */
+int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_status,
+                    void* stream);
+/* Device address of the 4-double scalar record {cost, cand_cost, status, spare} so the host
+ * side can all-reduce the two costs when points are sharded over ranks. */
+int ba_scalars_ptr(ba_handle h, double** scalars_dev);
+
+/* Per-observation residuals and Jacobians of the current state (bundle.py:251, :255-277),
+ * for Bundle.residuals()/Jresiduals() and stage-wise parity checks. */
+int ba_eval_observations(ba_handle h, void* stream);
+
+/* Copies one internal array to HOST memory (synchronises).  count = number of doubles. */
+int ba_get_array(ba_handle h, int which, double* dst_host, size_t count, void* stream);
+
+/* Stand-alone retraction used by update_motion/update_structure on host bundles
+ * (bundle_adjuster.py:334-343): cand <- state (+) (delta_cam, delta_pt), deltas are HOST
+ * arrays [n_opt_cam][6] / [n_opt_pt][3] (either may be NULL = no change). */
+int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt_host,
+               void* stream);
+
+/* Overwrite the reduced solution dC from a HOST array [n_opt_cam][6] -- lets the staged
+ * Python API call backsubstitute(dC) with a caller-supplied camera update (:316). */
+int ba_set_solution(ba_handle h, const double* dC_host, void* stream);
+
+int ba_sync(ba_handle h, void* stream);
+
+/* Number of kernel launches issued through this handle since creation (bench evidence). */
+long long ba_launch_count(ba_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BA_B200_H_ */

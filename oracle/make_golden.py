@@ -1,0 +1,266 @@
+"""TEST INFRASTRUCTURE ONLY -- generate ``tests/golden/*.npz`` from the UNMODIFIED reference.
+
+Run in the authoring container (needs ``/root/reference``):
+
+    python -m oracle.make_golden            # all small cases (seconds)
+    python -m oracle.make_golden --oleg N   # + N LM steps on data/oleg_synthetic (~1 min each)
+
+Every fixture stores (a) the scene as plain arrays (so tests need no reference on the GPU
+box) and (b) what the reference's own ``BundleAdjuster`` computed for it.  The reference is
+loaded through ``oracle/refshim.py`` (syntactic py2->py3 only).
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def scene_arrays(bundle):
+    """Reference Bundle -> plain arrays (all cameras, all tracks, every measurement)."""
+    Rs = np.array([c.R for c in bundle.cameras])
+    ts = np.array([c.t for c in bundle.cameras])
+    oc, ot, uv = [], [], []
+    for j, trk in enumerate(bundle.tracks):
+        for i in sorted(trk.measurements.keys()):
+            oc.append(i)
+            ot.append(j)
+            uv.append(np.asarray(trk.measurements[i], dtype=np.float64))
+    sm = bundle.sensor_model
+    if type(sm).__name__ == 'GaussianModel':
+        model_kind, model_param = 0, np.asarray(sm.cov, dtype=np.float64)
+    else:
+        model_kind, model_param = 1, np.array([[sm.sigma, 0.], [0., 0.]])
+    return dict(K=np.asarray(bundle.K, dtype=np.float64), Rs=Rs, ts=ts,
+                pts=np.asarray(bundle.reconstruction, dtype=np.float64),
+                obs_cam=np.asarray(oc, dtype=np.int64), obs_track=np.asarray(ot, dtype=np.int64),
+                obs_uv=np.asarray(uv, dtype=np.float64).reshape(-1, 2),
+                model_kind=np.int64(model_kind), model_param=model_param)
+
+
+def run_stages(ba_mod, bundle, damping, set_bundle_args=None, param_mask=None, tag=""):
+    """prepare -> damp -> schur -> solve -> backsub on the reference, every intermediate kept."""
+    out = {}
+    with quiet():
+        ba = ba_mod.BundleAdjuster()
+        ba.set_bundle(bundle, **(set_bundle_args or {}))
+    ba.prepare_schur_complement()
+    out['HCCs'] = ba.HCCs.copy()
+    out['HPPs'] = ba.HPPs.copy()
+    out['HCPs'] = ba.HCPs.copy()
+    out['bCs'] = ba.bCs.copy()
+    out['bPs'] = ba.bPs.copy()
+    ba.apply_damping(damping)
+    S, b = ba.compute_schur_complement()
+    out['S'] = S.copy()
+    out['b'] = b.copy()
+    out['HPP_invs'] = ba.HPP_invs.copy()
+    nc = len(ba.optim_camera_ids)
+    cam_mask = np.ones(6 * nc, bool) if param_mask is None else np.asarray(param_mask)[:6 * nc]
+    dC = ba.solve_motion_normal_eqns(S, b, cam_mask)
+    out['dC'] = dC.copy()
+    out['dP'] = ba.backsubstitute(dC).copy()
+    motion, structure = ba.compute_update(damping, param_mask)
+    out['motion'] = np.asarray(motion)
+    out['structure'] = np.asarray(structure)
+    out['cost'] = np.float64(ba.compute_cost(bundle))
+    with quiet():
+        bnext = bundle.clone_params()
+        ba.update_motion(motion, bnext)
+        ba.update_structure(structure, bnext)
+    out['cand_cost'] = np.float64(ba.compute_cost(bnext))
+    out['cand_Rs'] = np.array([c.R for c in bnext.cameras])
+    out['cand_ts'] = np.array([c.t for c in bnext.cameras])
+    out['cand_pts'] = np.asarray(bnext.reconstruction).copy()
+    out['damping'] = np.float64(damping)
+    out['camera_ids'] = np.asarray(list(ba.camera_ids), dtype=np.int64)
+    out['track_ids'] = np.asarray(list(ba.track_ids), dtype=np.int64)
+    out['optim_camera_indices'] = np.asarray(list(ba.optim_camera_indices), dtype=np.int64)
+    out['optim_track_indices'] = np.asarray(list(ba.optim_track_indices), dtype=np.int64)
+    if param_mask is not None:
+        out['param_mask'] = np.asarray(param_mask, dtype=bool)
+    return {tag + k: v for k, v in out.items()}
+
+
+def run_optimize(ba_mod, bundle, **kw):
+    with quiet():
+        ba = ba_mod.BundleAdjuster(bundle)
+        ba.optimize(**kw)
+    fb = ba.bundle
+    return dict(opt_costs=np.asarray(ba.costs, dtype=np.float64), opt_num_steps=np.int64(ba.num_steps),
+                opt_converged=np.bool_(ba.converged),
+                opt_Rs=np.array([c.R for c in fb.cameras]), opt_ts=np.array([c.t for c in fb.cameras]),
+                opt_pts=np.asarray(fb.reconstruction).copy(),
+                opt_complete_cost=np.float64(fb.complete_cost()))
+
+
+def save(name, **arrays):
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024.))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--oleg", type=int, default=0, help="LM steps to run on data/oleg_synthetic")
+    ap.add_argument("--only-oleg", action="store_true")
+    args = ap.parse_args()
+
+    refshim.install()
+    import bundle as rbundle
+    import bundle_adjuster as rba
+    import bundle_unittest as rbu
+    import sensor_model as rsm
+    import test_bundle as rtb
+    import schur as rschur
+    import optimize as roptimize
+    import lie as rlie
+
+    if not args.only_oleg:
+        # 1. the reference's own unit-test fixture: 4 cams, 10 pts, CauchyModel(0.05)
+        b = rbu.create_test_bundle()
+        d = scene_arrays(b)
+        d.update(run_stages(rba, b, 2.0, tag="d2_"))
+        d.update(run_stages(rba, b, 0.0, tag="d0_"))
+        # dense known answers of bundle_adjuster_unittest.py:16-67
+        r = b.residuals()
+        J = b.Jresiduals()[:, 6:]
+        JTJ, JTr = J.T.dot(J), J.T.dot(r)
+        n = 6 * (len(b.cameras) - 1)
+        A0, b0 = rschur.get_schur_complement(JTJ.copy(), JTr, n)
+        d['dense_S_d0'], d['dense_b_d0'] = A0, b0
+        JTJ2 = JTJ.copy()
+        roptimize.apply_lm_damping_inplace(JTJ2, 2.0)
+        d['dense_delta_d2'] = -np.linalg.solve(JTJ2, JTr)
+        d['complete_cost'] = np.float64(b.complete_cost())
+        d['residuals'] = r
+        d['Jresiduals'] = b.Jresiduals()
+        save("fixture_cauchy", **d)
+
+        # 2. same scene, GaussianModel(1.), + full optimize trace
+        b = rbu.create_test_bundle()
+        b.sensor_model = rsm.GaussianModel(1.)
+        d = scene_arrays(b)
+        d.update(run_stages(rba, b, 2.0, tag="d2_"))
+        d['complete_cost'] = np.float64(b.complete_cost())
+        d.update(run_optimize(rba, b, max_steps=25))
+        save("fixture_gaussian", **d)
+
+        # 3. anisotropic / full covariance Gaussian
+        for name, cov in (("fixture_gauss_diag", [2., 3.]), ("fixture_gauss_full", [[2., .5], [.5, 1.]])):
+            b = rbu.create_test_bundle()
+            b.sensor_model = rsm.GaussianModel(np.array(cov))
+            d = scene_arrays(b)
+            d.update(run_stages(rba, b, 0.5, tag="d_"))
+            save(name, **d)
+
+        # 4. camera/track subsets + masks (bundle_adjuster_unittest.py:70-119)
+        b = rbu.create_test_bundle()
+        d = scene_arrays(b)
+        sel = dict(camera_ids=[3, 1], track_ids=[0, 1, 2], camera_mask=[False, True],
+                   track_mask=[False, True, False])
+        d.update(run_stages(rba, b, 2.0, set_bundle_args=sel, tag="d2_"))
+        r = b.residuals_partial(sel['camera_ids'], sel['track_ids'])
+        J = b.Jresiduals_partial(sel['camera_ids'], sel['track_ids'])
+        JTJ, JTr = J.T.dot(J), J.T.dot(r)
+        roptimize.apply_lm_damping_inplace(JTJ, 2.0)
+        A, bb = rschur.get_schur_complement(JTJ, JTr, 12)
+        cpm = np.repeat(np.array(sel['camera_mask']), 6)
+        d['dense_S'] = A[cpm][:, cpm]
+        d['dense_b'] = bb[cpm]
+        save("fixture_subset", **d)
+        # 4b. subset by id lists rather than boolean masks, several optimised cameras
+        b = rbu.create_test_bundle()
+        d = scene_arrays(b)
+        sel = dict(camera_ids=[2, 0, 3], track_ids=[1, 3, 4, 5, 8], camera_mask=[3, 2],
+                   track_mask=[8, 1, 4])
+        d.update(run_stages(rba, b, 0.3, set_bundle_args=sel, tag="d_"))
+        save("fixture_subset_ids", **d)
+
+        # 5. param_mask freezing some camera parameters (bundle_adjuster.py:185-196,296-309)
+        b = rbu.create_test_bundle()
+        b.sensor_model = rsm.GaussianModel(1.)
+        d = scene_arrays(b)
+        pm = np.ones(6 * 3 + 3 * 10, bool)
+        pm[[0, 4, 5, 9, 17]] = False
+        d.update(run_stages(rba, b, 1.0, param_mask=pm, tag="d_"))
+        save("fixture_param_mask", **d)
+
+        # 6. pinv cutoff: one track seen by a single camera -> rank-2 point block at damping 0
+        b = rbu.create_test_bundle()
+        b.sensor_model = rsm.GaussianModel(1.)
+        for cid in (0, 2, 3):
+            b.tracks[6].measurements.pop(cid, None)
+        assert len(b.tracks[6].measurements) == 1
+        d = scene_arrays(b)
+        d.update(run_stages(rba, b, 0.0, tag="d0_"))
+        d.update(run_stages(rba, b, 1e-7, tag="dtiny_"))
+        d.update(run_stages(rba, b, 3.0, tag="d3_"))
+        save("fixture_rank_deficient", **d)
+
+        # 7. test_bundle.test_optimize_fast: 4 cams (pure rotation) x 12 pts, GaussianModel(.1)
+        with quiet():
+            b_true, b_init = rtb.create_test_problem(noise=0)
+        d = scene_arrays(b_init)
+        d.update(run_stages(rba, b_init, 10.0, tag="d10_"))
+        d.update(run_optimize(rba, b_init, max_steps=50))
+        save("planar_optimize", **d)
+
+        # 8. BASELINE config 1 from OUR generator (5 cams / 100 pts / k=4), reference results
+        from pysfm_b200 import synthetic
+        a = synthetic.make_arrays(**synthetic.CONFIGS["C1"])
+        nc, nt = len(a["Rs"]), len(a["pts"])
+        msm = np.zeros((nc, nt, 2))
+        mask = np.zeros((nc, nt), bool)
+        msm[a["obs_cam"], a["obs_track"]] = a["obs_uv"]
+        mask[a["obs_cam"], a["obs_track"]] = True
+        b = rbundle.Bundle.FromArrays(a["K"], a["Rs"], a["ts"], a["pts"], msm, mask)
+        d = scene_arrays(b)
+        d.update(run_stages(rba, b, 10.0, tag="d10_"))
+        d.update(run_stages(rba, b, 1e-3, tag="dsmall_"))
+        d.update(run_optimize(rba, b, max_steps=25))
+        save("config1_synthetic", **d)
+
+        # 9. lie.SO3.exp known answers (incl. the 1e-8 switch)
+        ms = np.array([[1., 3., -1.], [1e-9, 0., 0.], [0., 2e-8, 0.], [.1, -.2, .3], [0., 0., 0.],
+                       [3.0, 0.1, -0.2], [1e-4, 1e-4, -1e-4]])
+        save("so3_exp", ms=ms, Rs=np.array([rlie.SO3.exp(m) for m in ms]))
+
+    if args.oleg > 0:
+        import bundle_io as rio
+        droot = os.path.join(refshim.REFERENCE_ROOT, "data", "oleg_synthetic")
+        with quiet():
+            b = rio.load(os.path.join(droot, "tracks.txt"), os.path.join(droot, "poses.txt"))
+            b.triangulate_all()
+        d = scene_arrays(b)
+        d['obs_uv'] = d['obs_uv'].astype(np.int16)   # integer pixels in the data set
+        d['obs_cam'] = d['obs_cam'].astype(np.int16)
+        d['obs_track'] = d['obs_track'].astype(np.int16)
+        d['complete_cost'] = np.float64(b.complete_cost())
+        with quiet():
+            ba = rba.BundleAdjuster(b)
+        motion, structure = ba.compute_update(10.0)
+        d['d10_motion'], d['d10_structure'] = np.asarray(motion), np.asarray(structure)
+        d['d10_cost'] = np.float64(ba.compute_cost(b))
+        d.update(run_optimize(rba, b, max_steps=args.oleg))
+        save("oleg_synthetic", **d)
+
+
+if __name__ == "__main__":
+    main()

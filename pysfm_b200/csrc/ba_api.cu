@@ -1,0 +1,317 @@
+// C ABI of libba_b200.so -- see include/ba_b200.h for the contract and the reference
+// call sites each entry point replaces.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/ba_b200.h"
+#include "ba_context.h"
+
+using ba::Context;
+
+struct ba_context : public Context {};
+
+namespace {
+
+int fail_cuda(Context* c, cudaError_t e, const char* where) {
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s: %s", where, cudaGetErrorString(e));
+  if (c) c->last_error = buf;
+  return BA_ERR_CUDA;
+}
+
+#define BA_CUDA(c, call)                                     \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return fail_cuda((c), e__, #call); \
+  } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*p, 0, count * sizeof(T));
+}
+
+bool bound(const Context& c) {
+  return c.pt_ptr && c.obs_cam && c.obs_uv && c.cam_slot && c.pt_slot && c.state.cam_R &&
+         c.state.cam_t && c.state.pts;
+}
+
+int ensure_track_len(Context& c, cudaStream_t st) {
+  if (c.max_track_len > 0) return BA_OK;
+  std::vector<int> h((size_t)c.n_pt + 1);
+  BA_CUDA(&c, cudaMemcpyAsync(h.data(), c.pt_ptr, h.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  BA_CUDA(&c, cudaStreamSynchronize(st));
+  int m = 1;
+  for (int i = 0; i < c.n_pt; ++i) {
+    const int k = h[i + 1] - h[i];
+    if (k < 0) { c.last_error = "pt_ptr is not monotone"; return BA_ERR_BAD_ARGUMENT; }
+    if (k > m) m = k;
+  }
+  if (h[c.n_pt] != c.n_obs) { c.last_error = "pt_ptr[n_pt] != n_obs"; return BA_ERR_BAD_ARGUMENT; }
+  c.max_track_len = m;
+  return BA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ba_version(void) { return "ba_b200 0.1 (sm_100a, fp64)"; }
+
+const char* ba_last_error(ba_handle h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int ba_system_ld(int n) {
+  if (n < 1) n = 1;
+  return (n + ba::kSolveTile - 1) / ba::kSolveTile * ba::kSolveTile;
+}
+
+int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_opt_pt,
+              ba_handle* out) {
+  if (!out || n_cam < 1 || n_pt < 1 || n_obs < 0 || n_opt_cam < 0 || n_opt_cam > n_cam ||
+      n_opt_pt < 0 || n_opt_pt > n_pt)
+    return BA_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return BA_ERR_CUDA;
+  ba_context* c = new (std::nothrow) ba_context();
+  if (!c) return BA_ERR_CUDA;
+  c->device = device;
+  c->n_cam = n_cam; c->n_pt = n_pt; c->n_obs = n_obs;
+  c->n_opt_cam = n_opt_cam; c->n_opt_pt = n_opt_pt;
+  c->n_sys = 6 * n_opt_cam;
+  c->ld = ba_system_ld(c->n_sys);
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+    c->num_sms = sms;
+  c->partials_cap = c->num_sms * 32;
+  c->intr.K[0] = c->intr.K[4] = c->intr.K[8] = 1.0;  // Bundle default K = I (bundle.py:138)
+  c->model.kind = BA_MODEL_GAUSSIAN;                 // GaussianModel(1.) (bundle.py:139)
+  c->model.p[0] = 1.0; c->model.p[3] = 1.0;
+  bool ok = dev_alloc(&c->Vinv, (size_t)n_pt * 9) == cudaSuccess &&
+            dev_alloc(&c->bP, (size_t)n_pt * 3) == cudaSuccess &&
+            dev_alloc(&c->V, (size_t)n_pt * 9) == cudaSuccess &&
+            dev_alloc(&c->U, (size_t)n_cam * 36) == cudaSuccess &&
+            dev_alloc(&c->bC, (size_t)n_cam * 6) == cudaSuccess &&
+            dev_alloc(&c->dC, (size_t)c->ld) == cudaSuccess &&
+            dev_alloc(&c->dP, (size_t)n_pt * 3) == cudaSuccess &&
+            dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
+            dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
+            dev_alloc(&c->cam_mask, (size_t)c->ld) == cudaSuccess &&
+            dev_alloc(&c->partials, (size_t)c->partials_cap) == cudaSuccess &&
+            dev_alloc(&c->counters, (size_t)8 + 8192) == cudaSuccess &&
+            dev_alloc(&c->scalars, (size_t)1) == cudaSuccess;
+  if (!ok) {
+    ba_destroy(c);
+    return BA_ERR_CUDA;
+  }
+  *out = c;
+  return BA_OK;
+}
+
+int ba_destroy(ba_handle h) {
+  if (!h) return BA_OK;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->dC, h->dP, h->obs_r, h->obs_Jc,
+                  h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
+                  h->scalars};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete h;
+  return BA_OK;
+}
+
+int ba_set_intrinsics(ba_handle h, const double* K9) {
+  if (!h || !K9) return BA_ERR_BAD_ARGUMENT;
+  memcpy(h->intr.K, K9, 9 * sizeof(double));
+  return BA_OK;
+}
+
+int ba_set_sensor_model(ba_handle h, int kind, const double* p4) {
+  if (!h || !p4 || (kind != BA_MODEL_GAUSSIAN && kind != BA_MODEL_CAUCHY)) return BA_ERR_BAD_ARGUMENT;
+  h->model.kind = kind;
+  memcpy(h->model.p, p4, 4 * sizeof(double));
+  return BA_OK;
+}
+
+int ba_bind_structure(ba_handle h, const int* pt_ptr, const int* obs_cam, const double* obs_uv,
+                      const int* cam_slot, const int* pt_slot) {
+  if (!h || !pt_ptr || !obs_cam || !obs_uv || !cam_slot || !pt_slot) return BA_ERR_BAD_ARGUMENT;
+  if (((size_t)obs_uv & 15) != 0) { h->last_error = "obs_uv must be 16-byte aligned"; return BA_ERR_BAD_ARGUMENT; }
+  h->pt_ptr = pt_ptr; h->obs_cam = obs_cam; h->obs_uv = obs_uv;
+  h->cam_slot = cam_slot; h->pt_slot = pt_slot;
+  h->max_track_len = 0;
+  return BA_OK;
+}
+
+int ba_bind_state(ba_handle h, double* R, double* t, double* pts) {
+  if (!h || !R || !t || !pts) return BA_ERR_BAD_ARGUMENT;
+  h->state.cam_R = R; h->state.cam_t = t; h->state.pts = pts;
+  return BA_OK;
+}
+
+int ba_bind_candidate(ba_handle h, double* R, double* t, double* pts) {
+  if (!h || !R || !t || !pts) return BA_ERR_BAD_ARGUMENT;
+  h->cand.cam_R = R; h->cand.cam_t = t; h->cand.pts = pts;
+  return BA_OK;
+}
+
+int ba_bind_system(ba_handle h, double* sys) {
+  if (!h || !sys) return BA_ERR_BAD_ARGUMENT;
+  if (((size_t)sys & 15) != 0) { h->last_error = "sys must be 16-byte aligned"; return BA_ERR_BAD_ARGUMENT; }
+  h->sys = sys;
+  return BA_OK;
+}
+
+int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int flags, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h) || ((flags & BA_WANT_SCHUR) && !h->sys)) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_track_len(*h, st);
+  if (rc != BA_OK) return rc;
+  if ((flags & BA_WANT_BLOCKS) && !h->W) BA_CUDA(h, dev_alloc(&h->W, (size_t)h->n_obs * 18));
+  cudaError_t e = ba::launch_linearize_eliminate(*h, damping, pinv_rcond, flags, st);
+  if (e == cudaErrorInvalidValue) {
+    h->last_error = "track too long for the shared-memory elimination tile";
+    return BA_ERR_BAD_ARGUMENT;
+  }
+  BA_CUDA(h, e);
+  return BA_OK;
+}
+
+int ba_solve(ba_handle h, const unsigned char* mask_host, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!h->sys) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (mask_host && h->n_sys > 0)
+    BA_CUDA(h, cudaMemcpyAsync(h->cam_mask, mask_host, (size_t)h->n_sys, cudaMemcpyHostToDevice, st));
+  BA_CUDA(h, ba::launch_solve(*h, mask_host != nullptr, st));
+  return BA_OK;
+}
+
+int ba_backsub_retract_cost(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h) || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, ba::launch_backsub_retract_cost(*h, (cudaStream_t)stream));
+  return BA_OK;
+}
+
+int ba_cost(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h)) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, ba::launch_cost(*h, (cudaStream_t)stream));
+  return BA_OK;
+}
+
+int ba_accept(ba_handle h) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!h->cand.cam_R) return BA_ERR_NOT_BOUND;
+  ba::ParamSet t = h->state;
+  h->state = h->cand;
+  h->cand = t;
+  return BA_OK;
+}
+
+int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_status, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  ba::Scalars s;
+  BA_CUDA(h, cudaMemcpyAsync(&s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  if (cost) *cost = s.cost;
+  if (cand_cost) *cand_cost = s.cand_cost;
+  if (solve_status) *solve_status = (s.status != 0.0) ? BA_ERR_ILLCONDITIONED : BA_OK;
+  return BA_OK;
+}
+
+int ba_scalars_ptr(ba_handle h, double** p) {
+  if (!h || !p) return BA_ERR_BAD_ARGUMENT;
+  *p = reinterpret_cast<double*>(h->scalars);
+  return BA_OK;
+}
+
+int ba_eval_observations(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h)) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (!h->obs_r) {
+    BA_CUDA(h, dev_alloc(&h->obs_r, (size_t)h->n_obs * 2));
+    BA_CUDA(h, dev_alloc(&h->obs_Jc, (size_t)h->n_obs * 12));
+    BA_CUDA(h, dev_alloc(&h->obs_Jp, (size_t)h->n_obs * 6));
+  }
+  BA_CUDA(h, ba::launch_eval_observations(*h, (cudaStream_t)stream));
+  return BA_OK;
+}
+
+int ba_get_array(ba_handle h, int which, double* dst, size_t count, void* stream) {
+  if (!h || !dst) return BA_ERR_BAD_ARGUMENT;
+  const double* src = nullptr;
+  size_t n = 0;
+  switch (which) {
+    case BA_ARR_HCC: src = h->U; n = (size_t)h->n_cam * 36; break;
+    case BA_ARR_HPP: src = h->V; n = (size_t)h->n_pt * 9; break;
+    case BA_ARR_HCP: src = h->W; n = (size_t)h->n_obs * 18; break;
+    case BA_ARR_BC: src = h->bC; n = (size_t)h->n_cam * 6; break;
+    case BA_ARR_BP: src = h->bP; n = (size_t)h->n_pt * 3; break;
+    case BA_ARR_HPP_INV: src = h->Vinv; n = (size_t)h->n_pt * 9; break;
+    case BA_ARR_DC: src = h->dC; n = (size_t)h->n_sys; break;
+    case BA_ARR_DP: src = h->dP; n = (size_t)h->n_pt * 3; break;
+    case BA_ARR_RESIDUAL: src = h->obs_r; n = (size_t)h->n_obs * 2; break;
+    case BA_ARR_JC: src = h->obs_Jc; n = (size_t)h->n_obs * 12; break;
+    case BA_ARR_JP: src = h->obs_Jp; n = (size_t)h->n_obs * 6; break;
+    default: return BA_ERR_BAD_ARGUMENT;
+  }
+  if (!src) return BA_ERR_NOT_BOUND;
+  if (count != n) { h->last_error = "ba_get_array: wrong element count"; return BA_ERR_BAD_ARGUMENT; }
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (n) BA_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt_host, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h) || !h->cand.cam_R) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (delta_cam_host && h->n_opt_cam)
+    BA_CUDA(h, cudaMemcpyAsync(h->delta_cam, delta_cam_host, (size_t)h->n_opt_cam * 6 * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+  if (delta_pt_host && h->n_opt_pt)
+    BA_CUDA(h, cudaMemcpyAsync(h->delta_pt, delta_pt_host, (size_t)h->n_opt_pt * 3 * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+  BA_CUDA(h, ba::launch_retract(*h, delta_cam_host != nullptr, delta_pt_host != nullptr, st));
+  return BA_OK;
+}
+
+int ba_set_solution(ba_handle h, const double* dC_host, void* stream) {
+  if (!h || !dC_host) return BA_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (h->n_sys)
+    BA_CUDA(h, cudaMemcpyAsync(h->dC, dC_host, (size_t)h->n_sys * sizeof(double), cudaMemcpyHostToDevice, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+int ba_sync(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return BA_OK;
+}
+
+long long ba_launch_count(ba_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

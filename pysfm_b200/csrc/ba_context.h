@@ -1,0 +1,79 @@
+// Internal state behind the opaque ba_handle (see include/ba_b200.h).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+
+#include "ba_math.cuh"
+
+namespace ba {
+
+constexpr int kSolveTile = 64;  // Cholesky tile; the reduced system is padded to a multiple
+
+struct ParamSet {   // caller-owned device arrays
+  double* cam_R = nullptr;  // [n_cam][9]
+  double* cam_t = nullptr;  // [n_cam][3]
+  double* pts = nullptr;    // [n_pt][3]
+};
+
+// Scalar record kept in device memory; mirrored on the host by ba_read_scalars.
+struct Scalars {
+  double cost;        // compute_cost(current)
+  double cand_cost;   // compute_cost(candidate)
+  double status;      // 0 ok, 1 non-positive pivot in the reduced solve
+  double spare;
+};
+
+struct Context {
+  int device = 0;
+  int n_cam = 0, n_pt = 0, n_obs = 0, n_opt_cam = 0, n_opt_pt = 0;
+  int n_sys = 0;      // 6 * n_opt_cam
+  int ld = 0;         // padded leading dimension of S
+  int num_sms = 148;
+  int max_track_len = 0;  // longest track, fetched lazily from pt_ptr (sizes shared memory)
+
+  Intrinsics intr{};
+  ModelParams model{};
+
+  // bound, caller-owned
+  const int* pt_ptr = nullptr;
+  const int* obs_cam = nullptr;
+  const double* obs_uv = nullptr;
+  const int* cam_slot = nullptr;
+  const int* pt_slot = nullptr;
+  ParamSet state, cand;
+  double* sys = nullptr;  // [ld*ld + ld]
+
+  // library-owned workspace
+  double* Vinv = nullptr;   // [n_pt][9]   HPP_invs
+  double* bP = nullptr;     // [n_pt][3]   bPs
+  double* V = nullptr;      // [n_pt][9]   HPPs (undamped)       (BA_WANT_BLOCKS)
+  double* U = nullptr;      // [n_cam][36] HCCs (undamped)       (BA_WANT_BLOCKS)
+  double* bC = nullptr;     // [n_cam][6]  bCs                   (BA_WANT_BLOCKS)
+  double* W = nullptr;      // [n_obs][18] HCPs, lazily allocated (BA_WANT_BLOCKS)
+  double* dC = nullptr;     // [ld]        reduced solution
+  double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero)
+  double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
+  double* obs_Jc = nullptr; // [n_obs][12]
+  double* obs_Jp = nullptr; // [n_obs][6]
+  double* delta_cam = nullptr;  // [n_opt_cam][6] staging for ba_retract
+  double* delta_pt = nullptr;   // [n_pt][3]
+  unsigned char* cam_mask = nullptr;  // [ld] 1 = free parameter
+  double* partials = nullptr;   // per-CTA cost partial sums
+  unsigned int* counters = nullptr;  // last-CTA-done tickets
+  Scalars* scalars = nullptr;
+  int partials_cap = 0;
+
+  long long launches = 0;
+  std::string last_error;
+};
+
+// ---- kernel launchers (ba_kernels.cu / ba_solve.cu) ----
+cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond, int flags,
+                                       cudaStream_t st);
+cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st);
+cudaError_t launch_cost(Context& c, cudaStream_t st);
+cudaError_t launch_eval_observations(Context& c, cudaStream_t st);
+cudaError_t launch_retract(Context& c, bool have_cam, bool have_pt, cudaStream_t st);
+cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
+
+}  // namespace ba

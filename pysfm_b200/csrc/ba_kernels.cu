@@ -1,0 +1,515 @@
+// Observation-path kernels of the bundle-adjustment inner loop (sm_100a, FP64).
+//
+//   linearize_eliminate_kernel   prepare_schur_complement + apply_damping +
+//                                compute_schur_complement  (bundle_adjuster.py:211-278)
+//   retract_cameras_kernel       update_motion on the candidate (:334-337, bundle.py:76-80)
+//   backsub_cost_kernel          backsubstitute + update_structure + compute_cost(candidate)
+//                                (:316-331, :340-343, :165-171)
+//   cost_kernel                  compute_cost(current)            (:165-171)
+//   eval_observations_kernel     Bundle.residual / Jresidual dump (bundle.py:251-277)
+//
+// Work decomposition: the observation arrays are point-major CSR; one warp owns one point at
+// a time (grid-stride), lanes first span the point's observations (residual + Jacobians),
+// then span (observation, column) slots of the Schur outer products.  Everything a point
+// needs after its observations were read once stays in shared memory / registers; the only
+// global traffic besides the 20-byte observation records is the per-point Vinv/bP record and
+// the FP64 reductions into the L2-resident reduced system.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_context.h"
+
+namespace ba {
+
+// ------------------------------------------------------------------------------------------
+// shared argument block (passed by value in kernel parameter space)
+struct ObsArgs {
+  Intrinsics intr;
+  ModelParams model;
+  int n_cam, n_pt, n_obs;
+  const int* __restrict__ pt_ptr;
+  const int* __restrict__ obs_cam;
+  const double* __restrict__ obs_uv;
+  const int* __restrict__ cam_slot;
+  const int* __restrict__ pt_slot;
+  const double* __restrict__ cam_R;
+  const double* __restrict__ cam_t;
+  const double* __restrict__ pts;
+};
+
+// Deterministic grid-wide sum: every CTA deposits one partial, the last CTA to arrive adds
+// them in index order and stores the total.  `ticket` must be zero on entry and is reset.
+__device__ __forceinline__ void grid_sum_store(double warp_total, double* __restrict__ partials,
+                                               unsigned int* __restrict__ ticket,
+                                               double* __restrict__ out) {
+  __shared__ double s_warp[32];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) s_warp[wid] = warp_total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += s_warp[i];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int prev = atomicAdd(ticket, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) t += ((volatile double*)partials)[i];
+    *out = t;
+    *ticket = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct ElimArgs {
+  ObsArgs o;
+  double damping, rcond;
+  int ld, kcap;
+  double* __restrict__ sys;    // S [ld*ld] then rhs [ld]
+  double* __restrict__ Vinv;   // [n_pt][9]
+  double* __restrict__ bP;     // [n_pt][3]
+  double* __restrict__ V;      // [n_pt][9]   (blocks)
+  double* __restrict__ U;      // [n_cam][36] (blocks)
+  double* __restrict__ bC;     // [n_cam][6]  (blocks)
+  double* __restrict__ W;      // [n_obs][18] (blocks)
+  double* __restrict__ partials;
+  unsigned int* __restrict__ ticket;
+  double* __restrict__ cost_out;
+};
+
+// per-observation shared-memory record (doubles): Jc 12 | W 18 | Y 18 | jtr 6 | slot(1)
+constexpr int kObsRec = 12 + 18 + 18 + 6 + 1;
+
+template <bool WANT_BLOCKS, bool WANT_SCHUR>
+__global__ void __launch_bounds__(256)
+linearize_eliminate_kernel(const ElimArgs A) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  double* rec = smem + (size_t)wid * A.kcap * kObsRec;
+  const ObsArgs& o = A.o;
+  const double damp1 = 1.0 + A.damping;
+  double* __restrict__ S = A.sys;
+  double* __restrict__ rhs = A.sys + (size_t)A.ld * A.ld;
+
+  double cost_acc = 0.0;
+  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
+    const int beg = o.pt_ptr[pt];
+    const int k = o.pt_ptr[pt + 1] - beg;
+    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    const bool pt_free = o.pt_slot[pt] >= 0;
+    double Vl[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+
+    // ---- phase A: lanes over observations ------------------------------------------------
+    for (int a = lane; a < k; a += 32) {
+      const int ob = beg + a;
+      const int cam = o.obs_cam[ob];
+      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      const int slot = o.cam_slot[cam];
+      double r[2], Jc[12], Jp[6];
+      observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
+      Vl[0] += Jp[0] * Jp[0] + Jp[3] * Jp[3];
+      Vl[1] += Jp[0] * Jp[1] + Jp[3] * Jp[4];
+      Vl[2] += Jp[0] * Jp[2] + Jp[3] * Jp[5];
+      Vl[3] += Jp[1] * Jp[1] + Jp[4] * Jp[4];
+      Vl[4] += Jp[1] * Jp[2] + Jp[4] * Jp[5];
+      Vl[5] += Jp[2] * Jp[2] + Jp[5] * Jp[5];
+      bl[0] += Jp[0] * r[0] + Jp[3] * r[1];
+      bl[1] += Jp[1] * r[0] + Jp[4] * r[1];
+      bl[2] += Jp[2] * r[0] + Jp[5] * r[1];
+      if (slot >= 0 && pt_free) cost_acc += r[0] * r[0] + r[1] * r[1];
+      double* q = rec + (size_t)a * kObsRec;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) q[i] = Jc[i];
+      double Wl[18];
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) Wl[rr * 3 + m] = Jc[rr] * Jp[m] + Jc[6 + rr] * Jp[3 + m];
+#pragma unroll
+      for (int i = 0; i < 18; ++i) q[12 + i] = Wl[i];
+      double jtr[6];
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) {
+        jtr[rr] = Jc[rr] * r[0] + Jc[6 + rr] * r[1];
+        q[48 + rr] = jtr[rr];
+      }
+      reinterpret_cast<int*>(q + 54)[0] = slot;
+      if (WANT_BLOCKS) {
+        double* Uc = A.U + (size_t)cam * 36;
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc)
+            atomicAdd(Uc + rr * 6 + cc, Jc[rr] * Jc[cc] + Jc[6 + rr] * Jc[6 + cc]);
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) atomicAdd(A.bC + (size_t)cam * 6 + rr, jtr[rr]);
+        double* Wg = A.W + (size_t)ob * 18;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) Wg[i] = Wl[i];
+      }
+    }
+    // ---- phase B: point block ------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Vl[i] = warp_sum(Vl[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) bl[i] = warp_sum(bl[i]);
+    double Vf[9] = {Vl[0], Vl[1], Vl[2], Vl[1], Vl[3], Vl[4], Vl[2], Vl[4], Vl[5]};
+    if (lane == 0) {
+      if (WANT_BLOCKS) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A.V[(size_t)pt * 9 + i] = Vf[i];
+      }
+      A.bP[3 * pt] = bl[0]; A.bP[3 * pt + 1] = bl[1]; A.bP[3 * pt + 2] = bl[2];
+    }
+    if (!WANT_SCHUR) { __syncwarp(); continue; }
+    Vf[0] *= damp1; Vf[4] *= damp1; Vf[8] *= damp1;
+    double Vi[9];
+    sym3_pinv(Vf, A.rcond, Vi);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A.Vinv[(size_t)pt * 9 + i] = Vi[i];
+    }
+    __syncwarp();
+    // ---- phase C: Y = W Vinv rows, reduced right-hand side -------------------------------
+    for (int task = lane; task < 6 * k; task += 32) {
+      const int a = task / 6, rr = task - 6 * a;
+      double* q = rec + (size_t)a * kObsRec;
+      const double w0 = q[12 + rr * 3], w1 = q[12 + rr * 3 + 1], w2 = q[12 + rr * 3 + 2];
+      const double y0 = w0 * Vi[0] + w1 * Vi[3] + w2 * Vi[6];
+      const double y1 = w0 * Vi[1] + w1 * Vi[4] + w2 * Vi[7];
+      const double y2 = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
+      q[30 + rr * 3] = y0; q[30 + rr * 3 + 1] = y1; q[30 + rr * 3 + 2] = y2;
+      const int slot = reinterpret_cast<const int*>(q + 54)[0];
+      if (slot >= 0)
+        atomicAdd(rhs + 6 * slot + rr, q[48 + rr] - (y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
+    }
+    __syncwarp();
+    // ---- phase D: S_ab -= Y_a W_b^T (+ damped Jc^T Jc on the diagonal), a <= b -----------
+    for (int s0 = 0; s0 < 6 * k; s0 += 32) {
+      const int s = s0 + lane;
+      bool valid = s < 6 * k;
+      const int b = valid ? s / 6 : 0;
+      const int cc = valid ? s - 6 * b : 0;
+      const double* qb = rec + (size_t)b * kObsRec;
+      const double wb0 = qb[12 + cc * 3], wb1 = qb[12 + cc * 3 + 1], wb2 = qb[12 + cc * 3 + 2];
+      const double jb0 = qb[cc], jb1 = qb[6 + cc];
+      const int slot_b = reinterpret_cast<const int*>(qb + 54)[0];
+      valid = valid && slot_b >= 0;
+      const int bmax = min(k - 1, (s0 + 31) / 6);
+      for (int a = 0; a <= bmax; ++a) {
+        const double* qa = rec + (size_t)a * kObsRec;
+        const int slot_a = reinterpret_cast<const int*>(qa + 54)[0];
+        if (slot_a < 0) continue;  // warp-uniform
+        if (valid && a <= b) {
+          double* Srow = S + (size_t)(6 * slot_a) * A.ld + 6 * slot_b + cc;
+#pragma unroll
+          for (int rr = 0; rr < 6; ++rr) {
+            double val = -(qa[30 + rr * 3] * wb0 + qa[30 + rr * 3 + 1] * wb1 + qa[30 + rr * 3 + 2] * wb2);
+            if (a == b) {
+              const double d = qa[rr] * jb0 + qa[6 + rr] * jb1;
+              val += (rr == cc) ? d * damp1 : d;
+            }
+            atomicAdd(Srow + (size_t)rr * A.ld, val);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// cand cameras = state cameras (+) (-dC)      (update = -solution, bundle_adjuster.py:208)
+__global__ void retract_cameras_kernel(int n_cam, const int* __restrict__ cam_slot,
+                                       const double* __restrict__ R, const double* __restrict__ t,
+                                       const double* __restrict__ delta, double sign,
+                                       double* __restrict__ Rc, double* __restrict__ tc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cam) return;
+  const int slot = cam_slot[i];
+  if (slot < 0 || delta == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) Rc[9 * i + j] = R[9 * i + j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tc[3 * i + j] = t[3 * i + j];
+    return;
+  }
+  double d[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) d[j] = sign * delta[6 * slot + j];
+  camera_retract(R + 9 * i, t + 3 * i, d, Rc + 9 * i, tc + 3 * i);
+}
+
+__global__ void retract_points_kernel(int n_pt, const int* __restrict__ pt_slot,
+                                      const double* __restrict__ x, const double* __restrict__ delta,
+                                      double* __restrict__ xc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pt) return;
+  const int slot = pt_slot[i];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    xc[3 * i + j] = x[3 * i + j] + ((slot >= 0 && delta) ? delta[3 * slot + j] : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------
+struct BacksubArgs {
+  ObsArgs o;               // o.cam_R/cam_t/pts = CURRENT state (linearisation point)
+  const double* __restrict__ cand_R;
+  const double* __restrict__ cand_t;
+  double* __restrict__ cand_pts;
+  const double* __restrict__ dC;    // [6 n_opt_cam]
+  const double* __restrict__ Vinv;
+  const double* __restrict__ bP;
+  double* __restrict__ dP;          // [n_pt][3]
+  double* __restrict__ partials;
+  unsigned int* __restrict__ ticket;
+  double* __restrict__ cost_out;
+};
+
+__global__ void __launch_bounds__(256) backsub_cost_kernel(const BacksubArgs A) {
+  const ObsArgs& o = A.o;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  double cost_acc = 0.0;
+  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
+    const int beg = o.pt_ptr[pt];
+    const int k = o.pt_ptr[pt + 1] - beg;
+    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    const int pslot = o.pt_slot[pt];
+    double xc[3] = {x[0], x[1], x[2]};
+    if (pslot >= 0) {
+      // sum_j W_j^T dC_j  ==  sum_j Jp_j^T (Jc_j dC_j)
+      double acc[3] = {0, 0, 0};
+      for (int a = lane; a < k; a += 32) {
+        const int ob = beg + a;
+        const int cam = o.obs_cam[ob];
+        const int slot = o.cam_slot[cam];
+        if (slot < 0) continue;
+        const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+        double r[2], Jc[12], Jp[6];
+        observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
+        const double* d = A.dC + 6 * slot;
+        double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { q0 += Jc[j] * d[j]; q1 += Jc[6 + j] * d[j]; }
+#pragma unroll
+        for (int m = 0; m < 3; ++m) acc[m] += Jp[m] * q0 + Jp[3 + m] * q1;
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) acc[m] = warp_sum(acc[m]);
+      const double g0 = A.bP[3 * pt] - acc[0], g1 = A.bP[3 * pt + 1] - acc[1], g2 = A.bP[3 * pt + 2] - acc[2];
+      const double* Vi = A.Vinv + (size_t)pt * 9;
+      double dp[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) dp[m] = Vi[3 * m] * g0 + Vi[3 * m + 1] * g1 + Vi[3 * m + 2] * g2;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) xc[m] = x[m] - dp[m];
+      if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) A.dP[3 * pt + m] = dp[m];
+      }
+    } else if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) A.dP[3 * pt + m] = 0.0;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < 3; ++m) A.cand_pts[3 * pt + m] = xc[m];
+    }
+    if (pslot >= 0) {
+      for (int a = lane; a < k; a += 32) {
+        const int ob = beg + a;
+        const int cam = o.obs_cam[ob];
+        if (o.cam_slot[cam] < 0) continue;
+        const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+        double r[2];
+        residual_only(o.intr, o.model, A.cand_R + 9 * cam, A.cand_t + 3 * cam, xc, uv.x, uv.y, r);
+        cost_acc += r[0] * r[0] + r[1] * r[1];
+      }
+    }
+  }
+  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
+// ------------------------------------------------------------------------------------------
+struct CostArgs {
+  ObsArgs o;
+  double* __restrict__ partials;
+  unsigned int* __restrict__ ticket;
+  double* __restrict__ cost_out;
+};
+
+__global__ void __launch_bounds__(256) cost_kernel(const CostArgs A) {
+  const ObsArgs& o = A.o;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  double cost_acc = 0.0;
+  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
+    if (o.pt_slot[pt] < 0) continue;
+    const int beg = o.pt_ptr[pt];
+    const int k = o.pt_ptr[pt + 1] - beg;
+    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    for (int a = lane; a < k; a += 32) {
+      const int ob = beg + a;
+      const int cam = o.obs_cam[ob];
+      if (o.cam_slot[cam] < 0) continue;
+      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      double r[2];
+      residual_only(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r);
+      cost_acc += r[0] * r[0] + r[1] * r[1];
+    }
+  }
+  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
+// ------------------------------------------------------------------------------------------
+struct EvalArgs {
+  ObsArgs o;
+  double* __restrict__ r;   // [n_obs][2]
+  double* __restrict__ Jc;  // [n_obs][12]
+  double* __restrict__ Jp;  // [n_obs][6]
+};
+
+__global__ void __launch_bounds__(256) eval_observations_kernel(const EvalArgs A) {
+  const ObsArgs& o = A.o;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
+    const int beg = o.pt_ptr[pt];
+    const int k = o.pt_ptr[pt + 1] - beg;
+    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    for (int a = lane; a < k; a += 32) {
+      const int ob = beg + a;
+      const int cam = o.obs_cam[ob];
+      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      double r[2], Jc[12], Jp[6];
+      observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
+      A.r[2 * ob] = r[0]; A.r[2 * ob + 1] = r[1];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) A.Jc[(size_t)ob * 12 + i] = Jc[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) A.Jp[(size_t)ob * 6 + i] = Jp[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers
+static ObsArgs make_obs_args(const Context& c, const ParamSet& ps) {
+  ObsArgs o;
+  o.intr = c.intr;
+  o.model = c.model;
+  o.n_cam = c.n_cam; o.n_pt = c.n_pt; o.n_obs = c.n_obs;
+  o.pt_ptr = c.pt_ptr; o.obs_cam = c.obs_cam; o.obs_uv = c.obs_uv;
+  o.cam_slot = c.cam_slot; o.pt_slot = c.pt_slot;
+  o.cam_R = ps.cam_R; o.cam_t = ps.cam_t; o.pts = ps.pts;
+  return o;
+}
+
+static int point_grid(const Context& c, int warps_per_cta, int ctas_per_sm) {
+  const int want = (c.n_pt + warps_per_cta - 1) / warps_per_cta;
+  const int cap = c.num_sms * ctas_per_sm;
+  int g = want < cap ? want : cap;
+  if (g < 1) g = 1;
+  if (g > c.partials_cap) g = c.partials_cap;
+  return g;
+}
+
+cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond, int flags,
+                                       cudaStream_t st) {
+  const bool blocks = flags & 1, schur = flags & 2;
+  cudaError_t e;
+  if (schur) {
+    e = cudaMemsetAsync(c.sys, 0, ((size_t)c.ld * c.ld + c.ld) * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (blocks) {
+    if ((e = cudaMemsetAsync(c.U, 0, (size_t)c.n_cam * 36 * sizeof(double), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(c.bC, 0, (size_t)c.n_cam * 6 * sizeof(double), st)) != cudaSuccess) return e;
+  }
+  ElimArgs A;
+  A.o = make_obs_args(c, c.state);
+  A.damping = damping; A.rcond = rcond; A.ld = c.ld;
+  int kcap = c.max_track_len < 1 ? 1 : c.max_track_len;
+  A.kcap = kcap;
+  A.sys = c.sys; A.Vinv = c.Vinv; A.bP = c.bP; A.V = c.V; A.U = c.U; A.bC = c.bC; A.W = c.W;
+  A.partials = c.partials; A.ticket = c.counters; A.cost_out = &c.scalars->cost;
+  const size_t per_warp = (size_t)kcap * kObsRec * sizeof(double);
+  const size_t budget = 200 * 1024;
+  int warps = (int)(budget / per_warp);
+  if (warps < 1) return cudaErrorInvalidValue;  // track too long for the shared-memory tile
+  if (warps > 8) warps = 8;
+  const size_t smem = per_warp * warps;
+  int ctas_per_sm = (int)(budget / smem);
+  if (ctas_per_sm > 8 / warps * 4) ctas_per_sm = 8 / warps * 4;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int grid = point_grid(c, warps, ctas_per_sm);
+  auto kern = blocks ? (schur ? linearize_eliminate_kernel<true, true> : linearize_eliminate_kernel<true, false>)
+                     : (schur ? linearize_eliminate_kernel<false, true> : linearize_eliminate_kernel<false, false>);
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  kern<<<grid, warps * 32, smem, st>>>(A);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
+  {
+    const int tb = 128;
+    retract_cameras_kernel<<<(c.n_cam + tb - 1) / tb, tb, 0, st>>>(
+        c.n_cam, c.cam_slot, c.state.cam_R, c.state.cam_t, c.dC, -1.0, c.cand.cam_R, c.cand.cam_t);
+    c.launches += 1;
+  }
+  BacksubArgs A;
+  A.o = make_obs_args(c, c.state);
+  A.cand_R = c.cand.cam_R; A.cand_t = c.cand.cam_t; A.cand_pts = c.cand.pts;
+  A.dC = c.dC; A.Vinv = c.Vinv; A.bP = c.bP; A.dP = c.dP;
+  A.partials = c.partials; A.ticket = c.counters + 1; A.cost_out = &c.scalars->cand_cost;
+  const int grid = point_grid(c, 8, 8);
+  backsub_cost_kernel<<<grid, 256, 0, st>>>(A);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cost(Context& c, cudaStream_t st) {
+  CostArgs A;
+  A.o = make_obs_args(c, c.state);
+  A.partials = c.partials; A.ticket = c.counters; A.cost_out = &c.scalars->cost;
+  const int grid = point_grid(c, 8, 8);
+  cost_kernel<<<grid, 256, 0, st>>>(A);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval_observations(Context& c, cudaStream_t st) {
+  EvalArgs A;
+  A.o = make_obs_args(c, c.state);
+  A.r = c.obs_r; A.Jc = c.obs_Jc; A.Jp = c.obs_Jp;
+  const int grid = point_grid(c, 8, 8);
+  eval_observations_kernel<<<grid, 256, 0, st>>>(A);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_retract(Context& c, bool have_cam, bool have_pt, cudaStream_t st) {
+  const int tb = 128;
+  retract_cameras_kernel<<<(c.n_cam + tb - 1) / tb, tb, 0, st>>>(
+      c.n_cam, c.cam_slot, c.state.cam_R, c.state.cam_t, have_cam ? c.delta_cam : nullptr, 1.0,
+      c.cand.cam_R, c.cand.cam_t);
+  retract_points_kernel<<<(c.n_pt + tb - 1) / tb, tb, 0, st>>>(
+      c.n_pt, c.pt_slot, c.state.pts, have_pt ? c.delta_pt : nullptr, c.cand.pts);
+  c.launches += 2;
+  return cudaGetLastError();
+}
+
+}  // namespace ba

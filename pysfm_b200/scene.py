@@ -1,0 +1,325 @@
+"""Scene packing (host) and the device-resident problem (torch tensors + ba_handle).
+
+``pack_scene`` turns the reference's object graph (``Bundle.cameras[i].R/.t``,
+``Bundle.tracks[j].measurements``, ``Bundle.reconstruction``; bundle.py:54-146) plus the
+selection made by ``BundleAdjuster.set_bundle`` (bundle_adjuster.py:54-101) into the SoA /
+CSR arrays described in include/ba_b200.h.  ``DeviceProblem`` owns those arrays as torch
+CUDA tensors (torch is only the device-memory holder and stream provider) and forwards
+every numerical step to libba_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class PackedScene(object):
+    """Host-side SoA image of the selected sub-problem."""
+    __slots__ = ("camera_ids", "track_ids", "optim_camera_indices", "optim_track_indices",
+                 "K", "model_kind", "model_params", "cam_R", "cam_t", "pts",
+                 "pt_ptr", "obs_cam", "obs_uv", "obs_track", "cam_slot", "pt_slot")
+
+    @property
+    def n_cam(self):
+        return len(self.camera_ids)
+
+    @property
+    def n_pt(self):
+        return len(self.track_ids)
+
+    @property
+    def n_obs(self):
+        return int(self.obs_cam.shape[0])
+
+    @property
+    def n_opt_cam(self):
+        return len(self.optim_camera_indices)
+
+    @property
+    def n_opt_pt(self):
+        return len(self.optim_track_indices)
+
+    def shard(self, rank, world_size):
+        """Contiguous point range for `rank`, balanced by observation count (cameras, K and
+        the sensor model are replicated).  Returns a new PackedScene sharing camera arrays."""
+        if world_size == 1:
+            return self
+        nobs = self.n_obs
+        targets = [(nobs * r) // world_size for r in range(world_size + 1)]
+        cuts = np.searchsorted(self.pt_ptr, targets, side="left")
+        cuts[0], cuts[-1] = 0, self.n_pt
+        lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+        out = PackedScene()
+        for name in ("camera_ids", "optim_camera_indices", "K", "model_kind", "model_params",
+                     "cam_R", "cam_t", "cam_slot"):
+            setattr(out, name, getattr(self, name))
+        out.track_ids = list(self.track_ids[lo:hi])
+        o0, o1 = int(self.pt_ptr[lo]), int(self.pt_ptr[hi])
+        out.pts = np.ascontiguousarray(self.pts[lo:hi])
+        out.pt_ptr = (self.pt_ptr[lo:hi + 1] - o0).astype(np.int32)
+        out.obs_cam = np.ascontiguousarray(self.obs_cam[o0:o1])
+        out.obs_uv = np.ascontiguousarray(self.obs_uv[o0:o1])
+        out.obs_track = np.ascontiguousarray(self.obs_track[o0:o1] - lo)
+        # local point slots are renumbered densely; the global slot of local point p is
+        # recoverable from optim_track_indices (kept in global numbering)
+        local = self.pt_slot[lo:hi]
+        out.optim_track_indices = [int(i) for i in np.nonzero(local >= 0)[0]]
+        ps = np.full(hi - lo, -1, dtype=np.int32)
+        ps[out.optim_track_indices] = np.arange(len(out.optim_track_indices), dtype=np.int32)
+        out.pt_slot = ps
+        return out
+
+
+def _observation_arrays(bundle, camera_ids, track_ids):
+    """(obs_track_pos, obs_cam_pos, obs_uv) for every measurement of a selected track in a
+    selected camera -- the set prepare_schur_complement visits (bundle_adjuster.py:224-227)."""
+    cam_pos = {cid: p for p, cid in enumerate(camera_ids)}
+    fast = getattr(bundle, "_obs_arrays", None)
+    if fast is not None:
+        o_cam, o_trk, o_uv = fast
+        cam_lut = np.full(len(bundle.cameras), -1, dtype=np.int64)
+        cam_lut[np.asarray(camera_ids, dtype=np.int64)] = np.arange(len(camera_ids))
+        trk_lut = np.full(bundle.num_tracks(), -1, dtype=np.int64)
+        trk_lut[np.asarray(track_ids, dtype=np.int64)] = np.arange(len(track_ids))
+        cp, tp = cam_lut[o_cam], trk_lut[o_trk]
+        keep = (cp >= 0) & (tp >= 0)
+        return tp[keep], cp[keep], np.asarray(o_uv, dtype=np.float64)[keep]
+    t_list, c_list, uv_list = [], [], []
+    for tpos, tid in enumerate(track_ids):
+        for cid, z in bundle.tracks[tid].measurements.items():
+            p = cam_pos.get(cid)
+            if p is not None:
+                t_list.append(tpos)
+                c_list.append(p)
+                uv_list.append(z)
+    return (np.asarray(t_list, dtype=np.int64), np.asarray(c_list, dtype=np.int64),
+            np.asarray(uv_list, dtype=np.float64).reshape(-1, 2))
+
+
+def pack_scene(bundle, camera_ids, track_ids, optim_camera_indices, optim_track_indices):
+    s = PackedScene()
+    s.camera_ids = list(camera_ids)
+    s.track_ids = list(track_ids)
+    s.optim_camera_indices = [int(i) for i in optim_camera_indices]
+    s.optim_track_indices = [int(i) for i in optim_track_indices]
+    nc, nt = len(s.camera_ids), len(s.track_ids)
+    s.K = np.ascontiguousarray(np.asarray(bundle.K, dtype=np.float64).reshape(9))
+    s.model_kind, s.model_params = bundle.sensor_model.device_params()
+    s.model_params = np.ascontiguousarray(s.model_params, dtype=np.float64)
+    s.cam_R, s.cam_t = bundle.camera_arrays(s.camera_ids)
+    s.pts = np.ascontiguousarray(np.asarray(bundle.reconstruction, dtype=np.float64)[s.track_ids])
+    s.cam_slot = np.full(nc, -1, dtype=np.int32)
+    s.cam_slot[s.optim_camera_indices] = np.arange(len(s.optim_camera_indices), dtype=np.int32)
+    s.pt_slot = np.full(nt, -1, dtype=np.int32)
+    s.pt_slot[s.optim_track_indices] = np.arange(len(s.optim_track_indices), dtype=np.int32)
+
+    o_trk, o_cam, o_uv = _observation_arrays(bundle, s.camera_ids, s.track_ids)
+    # point-major; inside a point: fixed cameras first, then ascending reduced-system slot
+    order = np.lexsort((o_cam, s.cam_slot[o_cam], o_trk)) if len(o_trk) else np.zeros(0, np.int64)
+    o_trk, o_cam, o_uv = o_trk[order], o_cam[order], o_uv[order]
+    counts = np.bincount(o_trk, minlength=nt) if len(o_trk) else np.zeros(nt, np.int64)
+    s.pt_ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+    s.obs_cam = o_cam.astype(np.int32)
+    s.obs_track = o_trk.astype(np.int32)
+    s.obs_uv = np.ascontiguousarray(o_uv, dtype=np.float64)
+    return s
+
+
+def _as_vp(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class DeviceProblem(object):
+    """One packed sub-problem resident on one GPU, driven through the C ABI."""
+
+    def __init__(self, scene, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.BAError("pysfm_b200 needs a CUDA device: the bundle-adjustment path has no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.scene = scene
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        dev = self.device
+        self.n_sys = 6 * scene.n_opt_cam
+        self.ld = int(self.lib.ba_system_ld(self.n_sys))
+        tt = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+        self.pt_ptr = tt(scene.pt_ptr, torch.int32)
+        self.obs_cam = tt(scene.obs_cam, torch.int32) if scene.n_obs else torch.zeros(1, dtype=torch.int32, device=dev)
+        self.obs_uv = tt(scene.obs_uv, torch.float64) if scene.n_obs else torch.zeros(2, dtype=torch.float64, device=dev)
+        self.cam_slot = tt(scene.cam_slot, torch.int32)
+        self.pt_slot = tt(scene.pt_slot, torch.int32)
+        self.params = [dict(R=tt(scene.cam_R, torch.float64), t=tt(scene.cam_t, torch.float64),
+                            x=tt(scene.pts, torch.float64)) for _ in range(2)]
+        self.cur = 0
+        self.sys = torch.zeros(self.ld * self.ld + self.ld, dtype=torch.float64, device=dev)
+        h = ctypes.c_void_p()
+        rc = self.lib.ba_create(dev.index or 0, scene.n_cam, scene.n_pt, scene.n_obs, scene.n_opt_cam,
+                                scene.n_opt_pt, ctypes.byref(h))
+        _lib.check(None, rc, "ba_create")
+        self.h = h
+        K = np.ascontiguousarray(scene.K, dtype=np.float64)
+        self._chk(self.lib.ba_set_intrinsics(h, K.ctypes.data_as(ctypes.POINTER(ctypes.c_double))), "ba_set_intrinsics")
+        mp = np.ascontiguousarray(scene.model_params, dtype=np.float64)
+        self._chk(self.lib.ba_set_sensor_model(h, int(scene.model_kind), mp.ctypes.data_as(ctypes.POINTER(ctypes.c_double))),
+                  "ba_set_sensor_model")
+        self._chk(self.lib.ba_bind_structure(h, _as_vp(self.pt_ptr), _as_vp(self.obs_cam), _as_vp(self.obs_uv),
+                                             _as_vp(self.cam_slot), _as_vp(self.pt_slot)), "ba_bind_structure")
+        self._bind_params()
+        self._chk(self.lib.ba_bind_system(h, _as_vp(self.sys)), "ba_bind_system")
+        sp = ctypes.c_void_p()
+        self._chk(self.lib.ba_scalars_ptr(h, ctypes.byref(sp)), "ba_scalars_ptr")
+        self._scalars_ptr = sp.value
+
+    # -- plumbing --------------------------------------------------------------------------
+    def _chk(self, rc, what):
+        _lib.check(self.h, rc, what)
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _bind_params(self):
+        s, c = self.params[self.cur], self.params[1 - self.cur]
+        self._chk(self.lib.ba_bind_state(self.h, _as_vp(s["R"]), _as_vp(s["t"]), _as_vp(s["x"])), "ba_bind_state")
+        self._chk(self.lib.ba_bind_candidate(self.h, _as_vp(c["R"]), _as_vp(c["t"]), _as_vp(c["x"])), "ba_bind_candidate")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.ba_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state -----------------------------------------------------------------------------
+    @property
+    def state(self):
+        return self.params[self.cur]
+
+    @property
+    def candidate(self):
+        return self.params[1 - self.cur]
+
+    def upload_state(self, cam_R, cam_t, pts, non_blocking=False):
+        torch = self.torch
+        s = self.state
+        s["R"].copy_(torch.as_tensor(cam_R).reshape(s["R"].shape), non_blocking=non_blocking)
+        s["t"].copy_(torch.as_tensor(cam_t).reshape(s["t"].shape), non_blocking=non_blocking)
+        s["x"].copy_(torch.as_tensor(pts).reshape(s["x"].shape), non_blocking=non_blocking)
+
+    def download(self, which="state"):
+        p = self.state if which == "state" else self.candidate
+        return (p["R"].cpu().numpy().reshape(-1, 3, 3), p["t"].cpu().numpy().reshape(-1, 3),
+                p["x"].cpu().numpy().reshape(-1, 3))
+
+    # -- stages ----------------------------------------------------------------------------
+    def linearize_eliminate(self, damping, rcond, flags):
+        self._chk(self.lib.ba_linearize_eliminate(self.h, float(damping), float(rcond), int(flags), self._stream()),
+                  "ba_linearize_eliminate")
+
+    def solve(self, cam_param_mask=None):
+        if cam_param_mask is None:
+            mp = None
+        else:
+            m = np.ascontiguousarray(cam_param_mask, dtype=np.uint8)
+            assert m.shape == (self.n_sys,), 'shape was ' + str(m.shape)
+            self._mask_keepalive = m
+            mp = m.ctypes.data_as(ctypes.c_void_p)
+        self._chk(self.lib.ba_solve(self.h, mp, self._stream()), "ba_solve")
+
+    def backsub_retract_cost(self):
+        self._chk(self.lib.ba_backsub_retract_cost(self.h, self._stream()), "ba_backsub_retract_cost")
+
+    def cost(self):
+        self._chk(self.lib.ba_cost(self.h, self._stream()), "ba_cost")
+
+    def eval_observations(self):
+        self._chk(self.lib.ba_eval_observations(self.h, self._stream()), "ba_eval_observations")
+
+    def accept(self):
+        self._chk(self.lib.ba_accept(self.h), "ba_accept")
+        self.cur = 1 - self.cur
+
+    def retract(self, delta_cam=None, delta_pt=None):
+        dc = dp = None
+        keep = []
+        if delta_cam is not None:
+            a = np.ascontiguousarray(delta_cam, dtype=np.float64)
+            assert a.shape == (self.scene.n_opt_cam, 6), 'shape was ' + str(a.shape)
+            keep.append(a)
+            dc = a.ctypes.data_as(ctypes.c_void_p)
+        if delta_pt is not None:
+            a = np.ascontiguousarray(delta_pt, dtype=np.float64)
+            assert a.shape == (self.scene.n_opt_pt, 3), 'shape was ' + str(a.shape)
+            keep.append(a)
+            dp = a.ctypes.data_as(ctypes.c_void_p)
+        self._chk(self.lib.ba_retract(self.h, dc, dp, self._stream()), "ba_retract")
+        self._chk(self.lib.ba_sync(self.h, self._stream()), "ba_sync")
+        del keep
+
+    def set_solution(self, dC):
+        a = np.ascontiguousarray(dC, dtype=np.float64)
+        assert a.shape == (self.scene.n_opt_cam, 6), 'shape was ' + str(a.shape)
+        self._chk(self.lib.ba_set_solution(self.h, a.ctypes.data_as(ctypes.c_void_p), self._stream()), "ba_set_solution")
+
+    def upload_system(self, A, b):
+        """Overwrite the bound reduced system with a caller-supplied dense symmetric A and b."""
+        n, ld = self.n_sys, self.ld
+        host = np.zeros(ld * ld + ld)
+        M = host[:ld * ld].reshape(ld, ld)
+        M[:n, :n] = np.triu(np.asarray(A, dtype=np.float64))
+        host[ld * ld:ld * ld + n] = np.asarray(b, dtype=np.float64).reshape(n)
+        self.sys.copy_(self.torch.as_tensor(host))
+
+    def copy_solution_to(self, out_dC, out_dP):
+        """D2H of the camera solution and the point update into caller (pinned) torch tensors."""
+        assert out_dC.numel() == self.n_sys and out_dP.numel() == 3 * self.scene.n_pt
+        self._chk(self.lib.ba_get_array(self.h, _lib.BA_ARR_DC, ctypes.c_void_p(out_dC.data_ptr()), self.n_sys,
+                                        self._stream()), "ba_get_array")
+        self._chk(self.lib.ba_get_array(self.h, _lib.BA_ARR_DP, ctypes.c_void_p(out_dP.data_ptr()),
+                                        3 * self.scene.n_pt, self._stream()), "ba_get_array")
+
+    def read_scalars(self):
+        cost, cand = ctypes.c_double(), ctypes.c_double()
+        status = ctypes.c_int()
+        self._chk(self.lib.ba_read_scalars(self.h, ctypes.byref(cost), ctypes.byref(cand), ctypes.byref(status),
+                                           self._stream()), "ba_read_scalars")
+        return cost.value, cand.value, status.value
+
+    def scalars_tensor(self):
+        """torch view of the device scalar record {cost, cand_cost, status, spare} (for the
+        cross-rank cost reduction when points are sharded)."""
+        torch = self.torch
+
+        class _Wrap(object):
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (4,), "typestr": "<f8", "data": (self._scalars_ptr, False),
+                                      "version": 2}
+        t = torch.as_tensor(w, device=self.device)
+        self._scalars_keepalive = w
+        return t
+
+    def get_array(self, which, shape):
+        out = np.empty(int(np.prod(shape)), dtype=np.float64)
+        self._chk(self.lib.ba_get_array(self.h, int(which), out.ctypes.data_as(ctypes.c_void_p), out.size,
+                                        self._stream()), "ba_get_array")
+        return out.reshape(shape)
+
+    def system(self):
+        """(A, b): A = dense symmetric (n_sys, n_sys) mirrored from the accumulated triangle."""
+        n, ld = self.n_sys, self.ld
+        host = self.sys.cpu().numpy()
+        M = host[:ld * ld].reshape(ld, ld)[:n, :n]      # row-major: valid where row <= col
+        A = np.triu(M) + np.triu(M, 1).T
+        # diagonal 6x6 blocks were written in full; keep them as written
+        for i in range(n // 6):
+            A[6 * i:6 * i + 6, 6 * i:6 * i + 6] = M[6 * i:6 * i + 6, 6 * i:6 * i + 6]
+        return A, host[ld * ld:ld * ld + n].copy()
+
+    def launch_count(self):
+        return int(self.lib.ba_launch_count(self.h))

@@ -1,0 +1,162 @@
+"""Pin the CPU oracle (oracle/ba_oracle.py) against the UNMODIFIED reference.
+
+Golden fixtures in tests/golden/ were produced by oracle/make_golden.py, which runs the
+reference's own BundleAdjuster (loaded through oracle/refshim.py).  Tolerance: 1e-11 relative
+on every intermediate (the restatement differs from the reference only in summation order).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_problem, relerr
+from oracle import ba_oracle, refshim
+
+TOL = 1e-11
+
+STAGE_CASES = [
+    ("fixture_cauchy", "d2_"), ("fixture_cauchy", "d0_"),
+    ("fixture_gaussian", "d2_"),
+    ("fixture_gauss_diag", "d_"), ("fixture_gauss_full", "d_"),
+    ("fixture_subset", "d2_"), ("fixture_subset_ids", "d_"),
+    ("fixture_param_mask", "d_"),
+    ("fixture_rank_deficient", "d0_"), ("fixture_rank_deficient", "dtiny_"), ("fixture_rank_deficient", "d3_"),
+    ("planar_optimize", "d10_"),
+    ("config1_synthetic", "d10_"), ("config1_synthetic", "dsmall_"),
+]
+
+
+@pytest.mark.parametrize("name,prefix", STAGE_CASES)
+def test_stages_match_reference(name, prefix):
+    g = load_golden(name)
+    P = golden_problem(g, prefix)
+    damping = float(g[prefix + "damping"])
+    blocks = ba_oracle.prepare(P)
+    assert relerr(blocks["HCCs"], g[prefix + "HCCs"]) < TOL
+    assert relerr(blocks["HPPs"], g[prefix + "HPPs"]) < TOL
+    assert relerr(ba_oracle.dense_HCPs(P, blocks["W"]), g[prefix + "HCPs"]) < TOL
+    assert relerr(blocks["bCs"], g[prefix + "bCs"]) < TOL
+    assert relerr(blocks["bPs"], g[prefix + "bPs"]) < TOL
+    ba_oracle.apply_damping(blocks, damping)
+    S, b, Vinv = ba_oracle.schur(P, blocks, 1e-5)
+    # truncated pseudo-inverses amplify roundoff by 1/cutoff
+    loose = 1e-7 if name == "fixture_rank_deficient" and prefix != "d3_" else TOL
+    assert relerr(Vinv, g[prefix + "HPP_invs"]) < loose
+    assert relerr(S, g[prefix + "S"]) < loose
+    assert relerr(b, g[prefix + "b"]) < loose
+    if damping < 1e-6:
+        return   # undamped reduced system is gauge-singular: its "solution" is not a known answer
+    mask = None
+    if (prefix + "param_mask") in g:
+        mask = g[prefix + "param_mask"][:6 * len(P.optim_cam)]
+    dC = ba_oracle.solve_motion(S, b, mask)
+    assert relerr(dC, g[prefix + "dC"]) < max(loose, 1e-9)
+    dP = ba_oracle.backsubstitute(P, blocks, Vinv, dC)
+    assert relerr(dP, g[prefix + "dP"]) < max(loose, 1e-9)
+    motion, structure = ba_oracle.compute_update(P, damping, mask)
+    assert relerr(motion, g[prefix + "motion"]) < max(loose, 1e-9)
+    assert relerr(structure, g[prefix + "structure"]) < max(loose, 1e-9)
+    assert abs(ba_oracle.compute_cost(P) - float(g[prefix + "cost"])) <= TOL * abs(float(g[prefix + "cost"]))
+    Pn = ba_oracle.apply_update(P, motion, structure)
+    cam_ids, trk_ids = g[prefix + "camera_ids"], g[prefix + "track_ids"]
+    assert relerr(Pn.R, g[prefix + "cand_Rs"][cam_ids]) < 1e-9
+    assert relerr(Pn.t, g[prefix + "cand_ts"][cam_ids]) < 1e-9
+    assert relerr(Pn.x, g[prefix + "cand_pts"][trk_ids]) < 1e-9
+    cc = float(g[prefix + "cand_cost"])
+    assert abs(ba_oracle.compute_cost(Pn) - cc) <= 1e-8 * abs(cc)
+
+
+def test_dense_known_answers():
+    """The reference's own unit tests: Schur path == explicit dense J^T J solve
+    (bundle_adjuster_unittest.py:16-67)."""
+    g = load_golden("fixture_cauchy")
+    P = golden_problem(g, "d0_")
+    blocks = ba_oracle.prepare(P)
+    S, b, _ = ba_oracle.schur(P, blocks, 1e-5)
+    nc = len(P.optim_cam)
+    A = S.transpose(0, 2, 1, 3).reshape(6 * nc, 6 * nc)
+    assert np.sum(np.square(A - g["dense_S_d0"])) < 1e-7       # numpy_test.assertArrayEqual
+    assert np.sum(np.square(b.reshape(-1) - g["dense_b_d0"])) < 1e-7
+    motion, structure = ba_oracle.compute_update(golden_problem(g, "d2_"), 2.0)
+    delta = np.concatenate((motion.reshape(-1), structure.reshape(-1)))
+    assert np.sum(np.square(delta - g["dense_delta_d2"])) < 1e-7
+    # survey section 4 golden numbers
+    assert abs(np.linalg.norm(motion) - 3.580993461507523e-02) < 1e-12
+    assert abs(np.linalg.norm(structure) - 4.367344362677722e-01) < 1e-12
+    assert abs(ba_oracle.compute_cost(P) - 4.849743388506833e+01) < 1e-10
+
+
+def test_subset_dense_known_answer():
+    g = load_golden("fixture_subset")
+    P = golden_problem(g, "d2_")
+    blocks = ba_oracle.prepare(P)
+    ba_oracle.apply_damping(blocks, 2.0)
+    S, b, _ = ba_oracle.schur(P, blocks, 1e-5)
+    assert S.shape == (1, 1, 6, 6)
+    assert np.sum(np.square(S[0, 0] - g["dense_S"])) < 1e-7
+    assert np.sum(np.square(b.reshape(-1) - g["dense_b"])) < 1e-7
+
+
+@pytest.mark.parametrize("name,max_steps", [("fixture_gaussian", 25), ("planar_optimize", 50),
+                                            ("config1_synthetic", 25)])
+def test_optimize_trace(name, max_steps):
+    g = load_golden(name)
+    prefix = [k for k in g if k.endswith("camera_ids")][0][:-len("camera_ids")]
+    P = golden_problem(g, prefix)
+    Pf, info = ba_oracle.optimize(P, max_steps=max_steps)
+    ref = g["opt_costs"]
+    assert len(info["costs"]) == len(ref)
+    assert info["num_steps"] == int(g["opt_num_steps"])
+    assert info["converged"] == bool(g["opt_converged"])
+    assert relerr(np.array(info["costs"]), ref) < 1e-7
+    assert relerr(Pf.R, g["opt_Rs"]) < 1e-6
+    assert relerr(Pf.x, g["opt_pts"]) < 1e-6
+
+
+def test_so3_exp():
+    g = load_golden("so3_exp")
+    for m, R in zip(g["ms"], g["Rs"]):
+        assert np.max(np.abs(ba_oracle.so3_exp(m) - R)) < 1e-15
+
+
+def test_oleg_fixture_if_present():
+    path = os.path.join(os.path.dirname(__file__), "golden", "oleg_synthetic.npz")
+    if not os.path.isfile(path):
+        pytest.skip("oleg_synthetic golden not generated")
+    g = load_golden("oleg_synthetic")
+    nc, nt = len(g["Rs"]), len(g["pts"])
+    P = ba_oracle.Problem(g["K"], g["Rs"], g["ts"], g["pts"], g["obs_cam"], g["obs_track"], g["obs_uv"],
+                          ('gaussian', ba_oracle.gaussian_L(g["model_param"])), np.arange(1, nc), np.arange(nt))
+    motion, structure = ba_oracle.compute_update(P, 10.0)
+    assert relerr(motion, g["d10_motion"]) < 1e-9
+    assert relerr(structure, g["d10_structure"]) < 1e-9
+    assert abs(ba_oracle.compute_cost(P) - float(g["d10_cost"])) < 1e-12 * float(g["d10_cost"])
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_live_reference_random_scene():
+    """Re-run the reference itself (authoring container only) on a fresh random scene."""
+    import contextlib
+    import io
+    refshim.install()
+    try:
+        import bundle as rbundle
+        import bundle_adjuster as rba
+        from pysfm_b200 import synthetic
+        a = synthetic.make_arrays(6, 40, 3, seed=77, noise=0.5)
+        nc, nt = 6, 40
+        msm = np.zeros((nc, nt, 2))
+        mask = np.zeros((nc, nt), bool)
+        msm[a["obs_cam"], a["obs_track"]] = a["obs_uv"]
+        mask[a["obs_cam"], a["obs_track"]] = True
+        b = rbundle.Bundle.FromArrays(a["K"], a["Rs"], a["ts"], a["pts"], msm, mask)
+        with contextlib.redirect_stdout(io.StringIO()):
+            adj = rba.BundleAdjuster(b)
+            motion, structure = adj.compute_update(0.7)
+        P = ba_oracle.Problem(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"],
+                              ('gaussian', np.eye(2)), np.arange(1, nc), np.arange(nt))
+        m2, s2 = ba_oracle.compute_update(P, 0.7)
+        assert relerr(m2, motion) < 1e-10
+        assert relerr(s2, structure) < 1e-10
+    finally:
+        refshim.uninstall()
