@@ -28,11 +28,14 @@
  *                        or -1 when the camera is held fixed
  *   pt_slot [n_pt]       position of the point in the structure update, or -1 when the
  *                        track is eliminated but not updated (track_mask semantics)
- *   sys     [ld*ld + ld] reduced camera system: S stored with leading dimension
- *                        ld = ba_system_ld(6*n_opt_cam); only the triangle {row<=col} in
- *                        row-major terms is accumulated (== column-major lower), followed by
- *                        the right-hand side b.  This is the one buffer that is all-reduced
- *                        across ranks when points are sharded.
+ *   sys     [ba_system_size(n_opt_cam)]  reduced camera system, PACKED: the upper block
+ *                        triangle of S as 6x6 row-major blocks (a, b), a <= b, block rows back
+ *                        to back (block index a*nc' - a(a-1)/2 + (b-a), 36 doubles each,
+ *                        diagonal blocks stored in full), followed by the right-hand side
+ *                        b [6 nc'].  This is the one buffer that is all-reduced across ranks
+ *                        when points are sharded (half the bytes of a dense matrix).  The
+ *                        solver expands it into a library-owned dense lower-triangular copy
+ *                        with leading dimension ba_system_ld(6 nc') before factoring.
  */
 #ifndef BA_B200_H_
 #define BA_B200_H_
@@ -84,6 +87,8 @@ const char* ba_last_error(ba_handle h); /* text of the last CUDA error seen by t
 
 /* Leading dimension used for an n x n reduced system (n padded up to the solver tile). */
 int ba_system_ld(int n);
+/* Number of doubles in the packed reduced-system buffer for n_opt_cam optimised cameras. */
+size_t ba_system_size(int n_opt_cam);
 
 /* Problem sizes are fixed per handle (set_bundle, bundle_adjuster.py:54-114). */
 int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_opt_pt,
@@ -101,7 +106,7 @@ int ba_bind_structure(ba_handle h, const int* pt_ptr_dev, const int* obs_cam_dev
 /* Current estimate and the candidate ("bnext", bundle_adjuster.py:143) parameter buffers. */
 int ba_bind_state(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts_dev);
 int ba_bind_candidate(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts_dev);
-/* Reduced system buffer [ld*ld + ld] doubles, see layout above. */
+/* Reduced system buffer, ba_system_size(n_opt_cam) doubles, see layout above. */
 int ba_bind_system(ba_handle h, double* sys_dev);
 
 /* prepare_schur_complement + apply_damping + compute_schur_complement in one pass over the
@@ -112,7 +117,7 @@ int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int f
                            void* stream);
 
 /* solve_motion_normal_eqns (bundle_adjuster.py:281-312): mirrors nothing, factors the
- * accumulated triangle in place (Cholesky) and solves for dC.  cam_param_mask_host is NULL or
+ * packed system (Cholesky of a dense copy; the bound buffer is left intact) and solves for dC.  cam_param_mask_host is NULL or
  * 6*n_opt_cam bytes (0 = parameter frozen, :296-309).  A non-positive pivot is recorded in
  * the scalars and reported by ba_read_scalars as BA_ERR_ILLCONDITIONED. */
 int ba_solve(ba_handle h, const unsigned char* cam_param_mask_host, void* stream);

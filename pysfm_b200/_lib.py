@@ -30,6 +30,7 @@ SIGNATURES = {
     "ba_version": (ctypes.c_char_p, []),
     "ba_last_error": (ctypes.c_char_p, [_vp]),
     "ba_system_ld": (ctypes.c_int, [ctypes.c_int]),
+    "ba_system_size": (ctypes.c_size_t, [ctypes.c_int]),
     "ba_create": (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.POINTER(_vp)]),
     "ba_destroy": (ctypes.c_int, [_vp]),
     "ba_set_intrinsics": (ctypes.c_int, [_vp, _c_double_p]),

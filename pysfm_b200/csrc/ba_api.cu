@@ -71,6 +71,12 @@ int ba_system_ld(int n) {
   return (n + ba::kSolveTile - 1) / ba::kSolveTile * ba::kSolveTile;
 }
 
+size_t ba_system_size(int n_opt_cam) {
+  if (n_opt_cam < 0) n_opt_cam = 0;
+  const size_t nc = (size_t)n_opt_cam;
+  return nc * (nc + 1) / 2 * 36 + 6 * nc;
+}
+
 int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_opt_pt,
               ba_handle* out) {
   if (!out || n_cam < 1 || n_pt < 1 || n_obs < 0 || n_opt_cam < 0 || n_opt_cam > n_cam ||
@@ -86,6 +92,8 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
   c->n_opt_cam = n_opt_cam; c->n_opt_pt = n_opt_pt;
   c->n_sys = 6 * n_opt_cam;
   c->ld = ba_system_ld(c->n_sys);
+  c->sys_len = ba_system_size(n_opt_cam);
+  const size_t T = (size_t)c->ld / ba::kSolveTile;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
     c->num_sms = sms;
@@ -99,12 +107,16 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->U, (size_t)n_cam * 36) == cudaSuccess &&
             dev_alloc(&c->bC, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->dC, (size_t)c->ld) == cudaSuccess &&
+            dev_alloc(&c->Adense, (size_t)c->ld * c->ld + c->ld) == cudaSuccess &&
+            dev_alloc(&c->LinvT, T * ba::kSolveTile * ba::kSolveTile) == cudaSuccess &&
+            dev_alloc(&c->solve_flags, T * T + T) == cudaSuccess &&
+            dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->dP, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->cam_mask, (size_t)c->ld) == cudaSuccess &&
             dev_alloc(&c->partials, (size_t)c->partials_cap) == cudaSuccess &&
-            dev_alloc(&c->counters, (size_t)8 + 8192) == cudaSuccess &&
+            dev_alloc(&c->counters, (size_t)8) == cudaSuccess &&
             dev_alloc(&c->scalars, (size_t)1) == cudaSuccess;
   if (!ok) {
     ba_destroy(c);
@@ -119,7 +131,7 @@ int ba_destroy(ba_handle h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->dC, h->dP, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->scalars};
+                  h->scalars, h->Adense, h->LinvT, h->solve_flags, h->solve_tickets};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete h;

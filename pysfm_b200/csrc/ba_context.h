@@ -27,7 +27,8 @@ struct Context {
   int device = 0;
   int n_cam = 0, n_pt = 0, n_obs = 0, n_opt_cam = 0, n_opt_pt = 0;
   int n_sys = 0;      // 6 * n_opt_cam
-  int ld = 0;         // padded leading dimension of S
+  int ld = 0;         // padded leading dimension of the dense copy the solver factors
+  size_t sys_len = 0; // doubles in the packed system buffer (blocks + rhs)
   int num_sms = 148;
   int max_track_len = 0;  // longest track, fetched lazily from pt_ptr (sizes shared memory)
 
@@ -41,7 +42,7 @@ struct Context {
   const int* cam_slot = nullptr;
   const int* pt_slot = nullptr;
   ParamSet state, cand;
-  double* sys = nullptr;  // [ld*ld + ld]
+  double* sys = nullptr;  // packed reduced system: upper 6x6 blocks, row by row, then rhs
 
   // library-owned workspace
   double* Vinv = nullptr;   // [n_pt][9]   HPP_invs
@@ -51,6 +52,13 @@ struct Context {
   double* bC = nullptr;     // [n_cam][6]  bCs                   (BA_WANT_BLOCKS)
   double* W = nullptr;      // [n_obs][18] HCPs, lazily allocated (BA_WANT_BLOCKS)
   double* dC = nullptr;     // [ld]        reduced solution
+  double* Adense = nullptr; // [ld*ld + ld] dense lower-triangular copy + rhs, factored in place
+  double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
+  unsigned int* solve_flags = nullptr;    // [T*T + T] tile / x_k ready flags (epoch valued)
+  unsigned int* solve_tickets = nullptr;  // [2] task tickets of the dataflow solver
+  unsigned int solve_epoch = 0;
+  bool solve_attr_set = false;
+  bool elim_attr_set[4] = {false, false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
   double* obs_Jc = nullptr; // [n_obs][12]
@@ -59,7 +67,7 @@ struct Context {
   double* delta_pt = nullptr;   // [n_pt][3]
   unsigned char* cam_mask = nullptr;  // [ld] 1 = free parameter
   double* partials = nullptr;   // per-CTA cost partial sums
-  unsigned int* counters = nullptr;  // last-CTA-done tickets
+  unsigned int* counters = nullptr;  // last-CTA-done tickets of the grid-wide cost sums
   Scalars* scalars = nullptr;
   int partials_cap = 0;
 

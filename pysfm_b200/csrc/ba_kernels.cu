@@ -69,8 +69,9 @@ __device__ __forceinline__ void grid_sum_store(double warp_total, double* __rest
 struct ElimArgs {
   ObsArgs o;
   double damping, rcond;
-  int ld, kcap;
-  double* __restrict__ sys;    // S [ld*ld] then rhs [ld]
+  int n_opt_cam, kcap;
+  size_t rhs_off;              // doubles of packed blocks before the right-hand side
+  double* __restrict__ sys;    // packed upper 6x6 blocks (row by row), then rhs [6 n_opt_cam]
   double* __restrict__ Vinv;   // [n_pt][9]
   double* __restrict__ bP;     // [n_pt][3]
   double* __restrict__ V;      // [n_pt][9]   (blocks)
@@ -96,7 +97,7 @@ linearize_eliminate_kernel(const ElimArgs A) {
   const ObsArgs& o = A.o;
   const double damp1 = 1.0 + A.damping;
   double* __restrict__ S = A.sys;
-  double* __restrict__ rhs = A.sys + (size_t)A.ld * A.ld;
+  double* __restrict__ rhs = A.sys + A.rhs_off;
 
   double cost_acc = 0.0;
   for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
@@ -140,7 +141,9 @@ linearize_eliminate_kernel(const ElimArgs A) {
         jtr[rr] = Jc[rr] * r[0] + Jc[6 + rr] * r[1];
         q[48 + rr] = jtr[rr];
       }
-      reinterpret_cast<int*>(q + 54)[0] = slot;
+      // packed row base: block (slot, b) lives at index rowbase + b, b >= slot
+      reinterpret_cast<int2*>(q + 54)[0] =
+          make_int2(slot, slot >= 0 ? slot * A.n_opt_cam - slot * (slot - 1) / 2 - slot : 0);
       if (WANT_BLOCKS) {
         double* Uc = A.U + (size_t)cam * 36;
 #pragma unroll
@@ -191,33 +194,42 @@ linearize_eliminate_kernel(const ElimArgs A) {
         atomicAdd(rhs + 6 * slot + rr, q[48 + rr] - (y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
     }
     __syncwarp();
-    // ---- phase D: S_ab -= Y_a W_b^T (+ damped Jc^T Jc on the diagonal), a <= b -----------
-    for (int s0 = 0; s0 < 6 * k; s0 += 32) {
+    // ---- phase D1: diagonal blocks  S_aa += damped Jc^T Jc - Y_a W_a^T ---------------------
+    // lanes span the 36 contiguous entries of each free camera's diagonal block
+    for (int task = lane; task < 36 * k; task += 32) {
+      const int a = task / 36, e = task - 36 * a;
+      const int rr = e / 6, cc = e - 6 * rr;
+      const double* q = rec + (size_t)a * kObsRec;
+      const int2 sb = reinterpret_cast<const int2*>(q + 54)[0];   // {slot, packed row base}
+      if (sb.x < 0) continue;
+      double d = q[rr] * q[cc] + q[6 + rr] * q[6 + cc];
+      if (rr == cc) d *= damp1;
+      d -= q[30 + rr * 3] * q[12 + cc * 3] + q[30 + rr * 3 + 1] * q[12 + cc * 3 + 1] +
+           q[30 + rr * 3 + 2] * q[12 + cc * 3 + 2];
+      atomicAdd(S + ((size_t)(sb.y + sb.x) * 36 + e), d);
+    }
+    // ---- phase D2: off-diagonal blocks  S_ab -= Y_a W_b^T, a < b (slots ascend inside a
+    // point, so (a, b) is always in the stored upper block triangle) -------------------------
+    for (int s0 = 6; s0 < 6 * k; s0 += 32) {   // b = 0 has no partner a < b
       const int s = s0 + lane;
       bool valid = s < 6 * k;
       const int b = valid ? s / 6 : 0;
       const int cc = valid ? s - 6 * b : 0;
       const double* qb = rec + (size_t)b * kObsRec;
       const double wb0 = qb[12 + cc * 3], wb1 = qb[12 + cc * 3 + 1], wb2 = qb[12 + cc * 3 + 2];
-      const double jb0 = qb[cc], jb1 = qb[6 + cc];
       const int slot_b = reinterpret_cast<const int*>(qb + 54)[0];
       valid = valid && slot_b >= 0;
-      const int bmax = min(k - 1, (s0 + 31) / 6);
-      for (int a = 0; a <= bmax; ++a) {
+      const int amax = min(k - 1, (s0 + 31) / 6);   // exclusive bound is b, checked per lane
+      for (int a = 0; a < amax; ++a) {
         const double* qa = rec + (size_t)a * kObsRec;
-        const int slot_a = reinterpret_cast<const int*>(qa + 54)[0];
-        if (slot_a < 0) continue;  // warp-uniform
-        if (valid && a <= b) {
-          double* Srow = S + (size_t)(6 * slot_a) * A.ld + 6 * slot_b + cc;
+        const int2 sa = reinterpret_cast<const int2*>(qa + 54)[0];
+        if (sa.x < 0) continue;  // warp-uniform
+        if (valid && a < b) {
+          double* dst = S + ((size_t)(sa.y + slot_b) * 36 + cc);
 #pragma unroll
-          for (int rr = 0; rr < 6; ++rr) {
-            double val = -(qa[30 + rr * 3] * wb0 + qa[30 + rr * 3 + 1] * wb1 + qa[30 + rr * 3 + 2] * wb2);
-            if (a == b) {
-              const double d = qa[rr] * jb0 + qa[6 + rr] * jb1;
-              val += (rr == cc) ? d * damp1 : d;
-            }
-            atomicAdd(Srow + (size_t)rr * A.ld, val);
-          }
+          for (int rr = 0; rr < 6; ++rr)
+            atomicAdd(dst + rr * 6,
+                      -(qa[30 + rr * 3] * wb0 + qa[30 + rr * 3 + 1] * wb1 + qa[30 + rr * 3 + 2] * wb2));
         }
       }
     }
@@ -431,7 +443,7 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   const bool blocks = flags & 1, schur = flags & 2;
   cudaError_t e;
   if (schur) {
-    e = cudaMemsetAsync(c.sys, 0, ((size_t)c.ld * c.ld + c.ld) * sizeof(double), st);
+    e = cudaMemsetAsync(c.sys, 0, c.sys_len * sizeof(double), st);
     if (e != cudaSuccess) return e;
   }
   if (blocks) {
@@ -440,7 +452,8 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   }
   ElimArgs A;
   A.o = make_obs_args(c, c.state);
-  A.damping = damping; A.rcond = rcond; A.ld = c.ld;
+  A.damping = damping; A.rcond = rcond; A.n_opt_cam = c.n_opt_cam;
+  A.rhs_off = c.sys_len - (size_t)c.n_sys;
   int kcap = c.max_track_len < 1 ? 1 : c.max_track_len;
   A.kcap = kcap;
   A.sys = c.sys; A.Vinv = c.Vinv; A.bP = c.bP; A.V = c.V; A.U = c.U; A.bC = c.bC; A.W = c.W;
@@ -457,7 +470,11 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   const int grid = point_grid(c, warps, ctas_per_sm);
   auto kern = blocks ? (schur ? linearize_eliminate_kernel<true, true> : linearize_eliminate_kernel<true, false>)
                      : (schur ? linearize_eliminate_kernel<false, true> : linearize_eliminate_kernel<false, false>);
-  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  const int variant = (blocks ? 2 : 0) + (schur ? 1 : 0);
+  if (!c.elim_attr_set[variant]) {   // opt in to the full shared-memory carve-out once
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
+    c.elim_attr_set[variant] = true;
+  }
   kern<<<grid, warps * 32, smem, st>>>(A);
   c.launches += 1;
   return cudaGetLastError();

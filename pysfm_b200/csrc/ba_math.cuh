@@ -181,19 +181,39 @@ __device__ __forceinline__ void jacobi_rotate(double A[3][3], double Q[3][3]) {
   }
 }
 
-// Pseudo-inverse of a symmetric 3x3 (V[9] row-major, symmetric) with numpy.linalg.pinv's
-// rule: eigen-directions whose |eigenvalue| <= rcond * max|eigenvalue| are dropped.
-// rcond < 0: plain inverse by cofactors (numpy.linalg.inv branch of the reference).
+// Inverse of a symmetric 3x3 by cofactors (only the upper triangle of V is read); the result
+// is exactly symmetric.
+__device__ __forceinline__ void sym3_inv(const double V[9], double det, double out[9]) {
+  const double id = 1.0 / det;
+  const double c00 = V[4] * V[8] - V[5] * V[5];
+  const double c01 = V[2] * V[5] - V[1] * V[8];
+  const double c02 = V[1] * V[5] - V[2] * V[4];
+  const double c11 = V[0] * V[8] - V[2] * V[2];
+  const double c12 = V[1] * V[2] - V[0] * V[5];
+  const double c22 = V[0] * V[4] - V[1] * V[1];
+  out[0] = c00 * id; out[1] = c01 * id; out[2] = c02 * id;
+  out[3] = out[1];   out[4] = c11 * id; out[5] = c12 * id;
+  out[6] = out[2];   out[7] = out[5];   out[8] = c22 * id;
+}
+
+// Pseudo-inverse of a symmetric positive semi-definite 3x3 (V[9] row-major, symmetric) with
+// numpy.linalg.pinv's rule: eigen-directions whose |eigenvalue| <= rcond * max|eigenvalue|
+// are dropped.  rcond < 0: plain inverse (numpy.linalg.inv branch of the reference).
+//
+// Fast path: for eigenvalues l1 <= l2 <= l3 of a PSD matrix, l1 = det/(l2 l3) >= 4 det/tr^2
+// and l3 <= tr, so det > rcond tr^3 proves l1 > rcond l3: nothing is truncated and the
+// pseudo-inverse IS the inverse.  Only blocks that fail this (conservative) test pay for the
+// Jacobi eigen-decomposition.
 __device__ __forceinline__ void sym3_pinv(const double V[9], double rcond, double out[9]) {
+  const double det = V[0] * (V[4] * V[8] - V[5] * V[5]) + V[1] * (V[2] * V[5] - V[1] * V[8]) +
+                     V[2] * (V[1] * V[5] - V[2] * V[4]);
   if (rcond < 0.0) {
-    const double c00 = V[4] * V[8] - V[5] * V[7];
-    const double c01 = V[5] * V[6] - V[3] * V[8];
-    const double c02 = V[3] * V[7] - V[4] * V[6];
-    const double det = V[0] * c00 + V[1] * c01 + V[2] * c02;
-    const double id = 1.0 / det;
-    out[0] = c00 * id; out[1] = (V[2] * V[7] - V[1] * V[8]) * id; out[2] = (V[1] * V[5] - V[2] * V[4]) * id;
-    out[3] = c01 * id; out[4] = (V[0] * V[8] - V[2] * V[6]) * id; out[5] = (V[2] * V[3] - V[0] * V[5]) * id;
-    out[6] = c02 * id; out[7] = (V[1] * V[6] - V[0] * V[7]) * id; out[8] = (V[0] * V[4] - V[1] * V[3]) * id;
+    sym3_inv(V, det, out);
+    return;
+  }
+  const double tr = V[0] + V[4] + V[8];
+  if (det > rcond * tr * tr * tr) {
+    sym3_inv(V, det, out);
     return;
   }
   double A[3][3] = {{V[0], V[1], V[2]}, {V[1], V[4], V[5]}, {V[2], V[5], V[8]}};

@@ -153,7 +153,8 @@ class DeviceProblem(object):
         self.params = [dict(R=tt(scene.cam_R, torch.float64), t=tt(scene.cam_t, torch.float64),
                             x=tt(scene.pts, torch.float64)) for _ in range(2)]
         self.cur = 0
-        self.sys = torch.zeros(self.ld * self.ld + self.ld, dtype=torch.float64, device=dev)
+        self.sys_len = int(self.lib.ba_system_size(scene.n_opt_cam))
+        self.sys = torch.zeros(max(self.sys_len, 2), dtype=torch.float64, device=dev)
         h = ctypes.c_void_p()
         rc = self.lib.ba_create(dev.index or 0, scene.n_cam, scene.n_pt, scene.n_obs, scene.n_opt_cam,
                                 scene.n_opt_pt, ctypes.byref(h))
@@ -266,13 +267,23 @@ class DeviceProblem(object):
         assert a.shape == (self.scene.n_opt_cam, 6), 'shape was ' + str(a.shape)
         self._chk(self.lib.ba_set_solution(self.h, a.ctypes.data_as(ctypes.c_void_p), self._stream()), "ba_set_solution")
 
+    def _packed_index(self):
+        """(rows, cols) of the dense matrix entry stored at every slot of the packed block
+        triangle (include/ba_b200.h): blocks (a, b), a <= b, row by row, 36 doubles each."""
+        nc = self.scene.n_opt_cam
+        a, b = np.triu_indices(nc)
+        rows = (6 * a)[:, None, None] + np.arange(6)[None, :, None] + np.zeros((1, 1, 6), dtype=np.int64)
+        cols = (6 * b)[:, None, None] + np.arange(6)[None, None, :] + np.zeros((1, 6, 1), dtype=np.int64)
+        return rows.reshape(-1), cols.reshape(-1)
+
     def upload_system(self, A, b):
         """Overwrite the bound reduced system with a caller-supplied dense symmetric A and b."""
-        n, ld = self.n_sys, self.ld
-        host = np.zeros(ld * ld + ld)
-        M = host[:ld * ld].reshape(ld, ld)
-        M[:n, :n] = np.triu(np.asarray(A, dtype=np.float64))
-        host[ld * ld:ld * ld + n] = np.asarray(b, dtype=np.float64).reshape(n)
+        n = self.n_sys
+        A = np.asarray(A, dtype=np.float64).reshape(n, n)
+        rows, cols = self._packed_index()
+        host = np.zeros(max(self.sys_len, 2))
+        host[:rows.size] = A[rows, cols]
+        host[rows.size:rows.size + n] = np.asarray(b, dtype=np.float64).reshape(n)
         self.sys.copy_(self.torch.as_tensor(host))
 
     def copy_solution_to(self, out_dC, out_dP):
@@ -311,15 +322,14 @@ class DeviceProblem(object):
         return out.reshape(shape)
 
     def system(self):
-        """(A, b): A = dense symmetric (n_sys, n_sys) mirrored from the accumulated triangle."""
-        n, ld = self.n_sys, self.ld
+        """(A, b): A = dense symmetric (n_sys, n_sys) rebuilt from the packed upper blocks."""
+        n = self.n_sys
         host = self.sys.cpu().numpy()
-        M = host[:ld * ld].reshape(ld, ld)[:n, :n]      # row-major: valid where row <= col
-        A = np.triu(M) + np.triu(M, 1).T
-        # diagonal 6x6 blocks were written in full; keep them as written
-        for i in range(n // 6):
-            A[6 * i:6 * i + 6, 6 * i:6 * i + 6] = M[6 * i:6 * i + 6, 6 * i:6 * i + 6]
-        return A, host[ld * ld:ld * ld + n].copy()
+        rows, cols = self._packed_index()
+        A = np.zeros((n, n))
+        A[cols, rows] = host[:rows.size]
+        A[rows, cols] = host[:rows.size]      # diagonal blocks are stored in full: keep as written
+        return A, host[rows.size:rows.size + n].copy()
 
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))

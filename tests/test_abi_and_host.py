@@ -31,6 +31,8 @@ def test_library_builds_and_exports_header_symbols():
     assert b"sm_100a" in lib.ba_version()
     lib.ba_system_ld.restype = ctypes.c_int
     assert lib.ba_system_ld(24) == 64 and lib.ba_system_ld(1194) == 1216 and lib.ba_system_ld(64) == 64
+    lib.ba_system_size.restype = ctypes.c_size_t
+    assert lib.ba_system_size(199) == 199 * 200 // 2 * 36 + 6 * 199 and lib.ba_system_size(0) == 0
 
 
 def test_library_is_sm100a_sass():
