@@ -56,6 +56,7 @@ struct Context {
   double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
   unsigned int* solve_flags = nullptr;    // [T*T + T] tile / x_k ready flags (epoch valued)
   unsigned int* solve_tickets = nullptr;  // [2] task tickets of the dataflow solver
+  unsigned long long* solve_trace = nullptr;  // debug timeline (BA_SOLVE_TRACE builds only)
   unsigned int solve_epoch = 0;
   bool solve_attr_set = false;
   bool elim_attr_set[4] = {false, false, false, false};

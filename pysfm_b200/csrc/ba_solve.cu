@@ -90,7 +90,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Optional per-task timeline (tools/microbench/solve_bench.cu defines BA_SOLVE_TRACE).
+#ifdef BA_SOLVE_TRACE
+#define BA_TRACE_DECL unsigned long long* trace;
+#define BA_TRACE(rec, slot)                                                        \
+  do {                                                                             \
+    if (g.trace && threadIdx.x == 0) {                                             \
+      unsigned long long gt__;                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                     \
+      g.trace[(size_t)(rec) * 8 + (slot)] = gt__;                                  \
+    }                                                                              \
+  } while (0)
+#define BA_TRACE_SET(rec, slot, v)                                                 \
+  do {                                                                             \
+    if (g.trace && threadIdx.x == 0) g.trace[(size_t)(rec) * 8 + (slot)] = (v);    \
+  } while (0)
+#else
+#define BA_TRACE_DECL
+#define BA_TRACE(rec, slot) do { } while (0)
+#define BA_TRACE_SET(rec, slot, v) do { } while (0)
+#endif
+
 struct CholArgs {
+  BA_TRACE_DECL
   double* __restrict__ A;         // [ld*ld] dense lower, column-major; overwritten by L
   double* __restrict__ rhs;       // [ld] b -> y (forward substitution)
   double* __restrict__ x;         // [ld] solution
@@ -109,55 +131,88 @@ __device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int ep
   }
 }
 
-// Stage the 64x64 tile whose (r, m) element is at src[m*ld + r] into smem dst[m*NB + r].
-__device__ __forceinline__ void stage_tile(double* dst, const double* src, int ld) {
+// Shared-memory operand tiles are stored k-major with a padded row of LDT doubles:
+// element (row r, contraction index m) of an operand lives at tile[m*LDT + r].  LDT = 68 makes
+// the DMMA fragment loads (lanes = 4 consecutive m x 8 consecutive r) bank-conflict free.
+constexpr int LDT = NB + 4;
+constexpr int kTileDoubles = NB * LDT;
+
+// Stage the 64x64 tile whose (r, m) element is at src[m*ld + r] into smem dst[m*LDT + r].
+__device__ __forceinline__ void stage_tile(double* dst, const double* src, size_t ld) {
   // 64 columns x 512 B; 16 B per cp.async; 2048 chunks / 256 threads = 8 each
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int chunk = it * kSolveThreads + threadIdx.x;
     const int m = chunk >> 5, r2 = (chunk & 31) * 2;
-    cp_async16(dst + m * NB + r2, src + (size_t)m * ld + r2);
+    cp_async16(dst + m * LDT + r2, src + (size_t)m * ld + r2);
   }
 }
 
-// acc[a][b] += sum_m P[m][4tr+a] * Q[m][4tc+b]
-__device__ __forceinline__ void tile_mma(double acc[4][4], const double* __restrict__ P,
-                                         const double* __restrict__ Q, int tr, int tc) {
-#pragma unroll 8
-  for (int m = 0; m < NB; ++m) {
-    const double2 a01 = *reinterpret_cast<const double2*>(P + m * NB + 4 * tr);
-    const double2 a23 = *reinterpret_cast<const double2*>(P + m * NB + 4 * tr + 2);
-    const double2 b01 = *reinterpret_cast<const double2*>(Q + m * NB + 4 * tc);
-    const double2 b23 = *reinterpret_cast<const double2*>(Q + m * NB + 4 * tc + 2);
-    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+// Register tile of one thread in the warp-level DMMA layout.  Warp w owns rows
+// R0 = 32 (w & 1) .. +31 and columns C0 = 16 (w >> 1) .. +15 of the 64x64 tile; inside it
+//   v[mi][ni][e]  <->  row R0 + 8 mi + (lane >> 2),  column C0 + 8 ni + 2 (lane & 3) + e.
+struct Frag {
+  double v[4][2][2];
+  __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] += av[a] * bv[b];
+      for (int ni = 0; ni < 2; ++ni) v[mi][ni][0] = v[mi][ni][1] = 0.0;
+  }
+};
+
+// acc += P^T Q over the 64-long contraction:  acc[r][c] += sum_m P[m*LDT + r] * Q[m*LDT + c]
+// (FP64 tensor-core path: mma.sync.m8n8k4.f64, SASS DMMA.8x8x4)
+__device__ __forceinline__ void tile_dmma(Frag& acc, const double* __restrict__ P,
+                                          const double* __restrict__ Q, int R0, int C0, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* pa = P + t4 * LDT + R0 + g;
+  const double* pb = Q + t4 * LDT + C0 + g;
+#pragma unroll 4
+  for (int m0 = 0; m0 < NB; m0 += 4) {
+    double a[4], b[2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) a[mi] = pa[m0 * LDT + 8 * mi];
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) b[ni] = pb[m0 * LDT + 8 * ni];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc.v[mi][ni][0]), "+d"(acc.v[mi][ni][1])
+                     : "d"(a[mi]), "d"(b[ni]));
   }
 }
 
 // Shared memory map (doubles):
-//   buf[2][2][NB*NB]   double-buffered operand tiles (P, Q) of the k loop            128 KB
+//   buf[4][NB*LDT]     double-buffered operand tiles (P, Q) of the k loop           136 KB
 //   aliases used after the k loop of a task:
-//     W  [NB][NBP]  = buf            diagonal tile being factored (full symmetric)
-//     M  [NB][NBP]  = buf + NB*NBP   running L~^{-1} (strict lower part)
-//     Cs [NB*NB]    = buf            panel task: C transposed to [m][r]
-//     Bs [NB*NB]    = buf + NB*NB    panel task: LinvT tile [m][c]
-//   vec[3][NB]      y_k staging, b_j accumulator, scratch
-constexpr int kSolveSmemDoubles = 4 * NB * NB + 4 * NB;
+//     LTs = buf                diagonal task: scaled L_jj^{-1}, transposed, [m][c]
+//     Cs  = buf                panel task: C transposed to [m][r]
+//     Bs  = buf + NB*LDT       panel task: LinvT tile [m][c]
+//   vec[8][NB]  u[2], um[2] (pivot rows of W and M, ping-pong), piv, isd, tvec, yk
+constexpr int kSolveSmemDoubles = 4 * kTileDoubles + 8 * NB;
 constexpr size_t kSolveSmemBytes = kSolveSmemDoubles * sizeof(double);
 
 __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const CholArgs g) {
   extern __shared__ __align__(16) double sm[];
   double* const buf = sm;
-  double* const vec = sm + 4 * NB * NB;
+  double* const vec = sm + 4 * kTileDoubles;
+  double* const u_buf = vec;             // [2][NB]
+  double* const um_buf = vec + 2 * NB;   // [2][NB]
+  double* const piv = vec + 4 * NB;
+  double* const isd = vec + 5 * NB;
+  double* const tvec = vec + 6 * NB;
+  double* const yk = vec + 7 * NB;
   __shared__ int s_task;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
-  const int tr = tid & 15, tc = tid >> 4;
-  const int T = g.T, ld = g.ld;
+  const int lane = tid & 31, wid = tid >> 5;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int R0 = 32 * (wid & 1), C0 = 16 * (wid >> 1);
+  const int T = g.T;
+  const size_t ld = (size_t)g.ld;
   const int ntasks = T * (T + 1) / 2;
   const unsigned int epoch = g.epoch;
 
@@ -171,7 +226,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // column-major enumeration of the lower triangle: column j holds T - j tasks
     int j = 0, rem = t;
     {
-      // solve rem < T - j incrementally from a closed-form guess
       const double Tf = (double)T + 0.5;
       j = (int)(Tf - sqrt(Tf * Tf - 2.0 * (double)t));
       if (j < 0) j = 0;
@@ -182,20 +236,19 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     }
     const int i = j + rem;
     const bool diag = (i == j);
+    BA_TRACE_SET(t, 0, ((unsigned long long)i << 32) | (unsigned)j);
+    BA_TRACE_SET(t, 1, (unsigned long long)blockIdx.x);
+    BA_TRACE(t, 2);   // task grabbed
 
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    Frag acc;
+    acc.zero();
     double bacc = 0.0;  // diag task, tid < NB: sum_k (L_jk y_k)[tid]
 
     // ---- k loop: acc += L_ik L_jk^T, operands double-buffered through cp.async ------------
-    // stage s of step k: P = buf + (2*(k&1))*NB*NB, Q = P + NB*NB (Q unused when diag)
     auto issue = [&](int k) {
-      double* P = buf + (size_t)(2 * (k & 1)) * NB * NB;
+      double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)i * NB, ld);
-      if (!diag) stage_tile(P + NB * NB, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
+      if (!diag) stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
       cp_async_commit();
     };
     if (j > 0) {
@@ -214,152 +267,166 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       } else {
         cp_async_wait<0>();
       }
-      if (diag && tid < NB) vec[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
+      if (diag && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
       __syncthreads();
-      const double* P = buf + (size_t)(2 * (k & 1)) * NB * NB;
-      const double* Q = diag ? P : P + NB * NB;
-      tile_mma(acc, P, Q, tr, tc);
+      const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+      const double* Q = diag ? P : P + kTileDoubles;
+      tile_dmma(acc, P, Q, R0, C0, lane);
       if (diag && tid < NB) {
         double s = 0.0;
 #pragma unroll 8
-        for (int m = 0; m < NB; ++m) s += P[m * NB + tid] * vec[m];
+        for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
         bacc += s;
       }
       __syncthreads();
     }
+    BA_TRACE(t, 3);   // k loop done
 
-    // ---- C = A_ij - acc ---------------------------------------------------------------------
     const double* Aij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
     if (diag) {
-      // Only the lower triangle of A_jj is valid in memory: build the full symmetric tile.
-      double* W = buf;
-      double* M = buf + NB * NBP;
+      // ---- W = A_jj - acc (full symmetric tile: only the lower triangle is valid in memory),
+      //      M = I;  both live in registers in the DMMA layout -------------------------------
+      Frag W, M;
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int r = 4 * tr + a, c = 4 * tc + b;
-          if (r >= c) {
-            const double v = __ldcg(Aij + (size_t)c * ld + r) - acc[a][b];
-            W[r * NBP + c] = v;
-            W[c * NBP + r] = v;
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
+            const int hi = r > c ? r : c, lo = r > c ? c : r;
+            W.v[mi][ni][e] = __ldcg(Aij + (size_t)lo * ld + hi) - acc.v[mi][ni][e];
+            M.v[mi][ni][e] = (r == c) ? 1.0 : 0.0;
           }
-          M[r * NBP + c] = 0.0;
-        }
       if (tid == 0) s_bad = 0;
-      // Gauss-Jordan sweep without pivoting: after step p row r > p of W holds the Schur
-      // complement in columns > p, and M (unit lower) accumulates L~^{-1}:  M A = U = D L~^T.
-      const int c = tid & 63, rg = tid >> 6;
+      // Gauss-Jordan sweep without pivoting.  After step p the rows r > p of W hold the Schur
+      // complement (kept symmetric, so column p equals row p) and M accumulates the unit
+      // lower-triangular L~^{-1}:  M A = U = D L~^T.  One barrier per step: the owners of row
+      // p+1 publish it (ping-pong buffers) right after their update of step p.
+      auto publish_row = [&](int p) {
+        double* u = u_buf + (p & 1) * NB;
+        double* um = um_buf + (p & 1) * NB;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+          if (R0 + 8 * mi + gq == p) {
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+              const int c = C0 + 8 * ni + 2 * t4;
+              *reinterpret_cast<double2*>(u + c) = make_double2(W.v[mi][ni][0], W.v[mi][ni][1]);
+              *reinterpret_cast<double2*>(um + c) = make_double2(M.v[mi][ni][0], M.v[mi][ni][1]);
+            }
+          }
+      };
+      publish_row(0);
       for (int p = 0; p < NB; ++p) {
         __syncthreads();
-        double d = W[p * NBP + p];
+        const double* u = u_buf + (p & 1) * NB;
+        const double* um = um_buf + (p & 1) * NB;
+        double d = u[p];
         if (!(d > 0.0)) {          // also catches NaN; uniform across the block
           if (tid == 0) s_bad = 1;
           d = 1.0;
         }
+        if (tid == 0) piv[p] = d;
         const double id = 1.0 / d;
-        if (c == p) {
-          for (int r = p + 1 + rg; r < NB; r += 4) M[r * NBP + p] = -W[r * NBP + p] * id;
-        } else if (c > p) {
-          const double u = W[p * NBP + c];
-          for (int r = p + 1 + rg; r < NB; r += 4) W[r * NBP + c] -= (W[r * NBP + p] * id) * u;
-        } else {
-          const double u = M[p * NBP + c];
-          for (int r = p + 1 + rg; r < NB; r += 4) M[r * NBP + c] -= (W[r * NBP + p] * id) * u;
+        double f[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const int r = R0 + 8 * mi + gq;
+          f[mi] = (r > p) ? u[r] * id : 0.0;
         }
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const int c = C0 + 8 * ni + 2 * t4;
+          const double2 uc = *reinterpret_cast<const double2*>(u + c);
+          const double2 mc = *reinterpret_cast<const double2*>(um + c);
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            W.v[mi][ni][0] -= f[mi] * uc.x;
+            W.v[mi][ni][1] -= f[mi] * uc.y;
+            M.v[mi][ni][0] -= f[mi] * mc.x;
+            M.v[mi][ni][1] -= f[mi] * mc.y;
+          }
+        }
+        if (p + 1 < NB) publish_row(p + 1);
       }
       __syncthreads();
-      if (s_bad) {
-        if (tid == 0) *g.status = 1.0;
-        // leave an identity factor behind so that dependants stay finite
-        for (int e = tid; e < NB * NB; e += kSolveThreads) {
-          const int r = e >> 6, cc = e & 63;
-          W[r * NBP + cc] = (r == cc) ? 1.0 : 0.0;
-          M[r * NBP + cc] = 0.0;
-        }
-        __syncthreads();
-      }
-      // scale: L[r][c] = U[c][r] / sqrt(U[c][c]) (r >= c);  Linv[r][c] = M[r][c] / sqrt(U[r][r])
-      double* isd = vec + NB;      // 1/sqrt(U[r][r])
-      if (tid < NB) {
-        isd[tid] = 1.0 / sqrt(W[tid * NBP + tid]);
-      }
+      BA_TRACE(t, 4);   // sweep done
+      const bool bad = s_bad != 0;
+      if (bad && tid == 0) *g.status = 1.0;
+      if (tid < NB) isd[tid] = bad ? 1.0 : 1.0 / sqrt(piv[tid]);
       __syncthreads();
-      double* Ljj = g.A + (size_t)(j * NB) * ld + (size_t)j * NB;
-      double* LT = g.LinvT + (size_t)j * NB * NB;
-      for (int e = tid; e < NB * NB; e += kSolveThreads) {
-        const int cc = e >> 6, r = e & 63;      // r fastest: coalesced column-major store
-        if (r >= cc) Ljj[(size_t)cc * ld + r] = W[cc * NBP + r] * isd[cc];
-        // LinvT[m = cc][c' = r] = Linv[r][cc]
-        double v = 0.0;
-        if (r > cc) v = M[r * NBP + cc] * isd[r];
-        else if (r == cc) v = isd[r];
-        LT[cc * NB + r] = v;
-      }
-      // forward substitution: y_j = Linv (b_j - bacc);  thread r: sum_m LinvT[m][r] t[m]
-      double* tvec = vec + 2 * NB;
+      // scaled inverse, transposed, into smem:  LTs[m*LDT + c'] = Linv[c'][m] = M[c'][m] isd[c']
+      // (on a failed pivot leave an identity behind so that dependants stay finite)
+      double* LTs = buf;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
+            double v = (c <= r) ? M.v[mi][ni][e] * isd[r] : 0.0;
+            if (bad) v = (r == c) ? 1.0 : 0.0;
+            LTs[c * LDT + r] = v;
+          }
       if (tid < NB) tvec[tid] = __ldcg(g.rhs + j * NB + tid) - bacc;
       __syncthreads();
+      double* LT = g.LinvT + (size_t)j * NB * NB;
+      for (int e = tid; e < NB * NB; e += kSolveThreads) LT[e] = LTs[(e >> 6) * LDT + (e & 63)];
+      // forward substitution: y_j = Linv (b_j - sum_k L_jk y_k);  thread r: sum_m LTs[m][r] t[m]
       if (tid < NB) {
         double s = 0.0;
-        for (int m = 0; m <= tid; ++m) {
-          const double li = (m == tid) ? isd[tid] : M[tid * NBP + m] * isd[tid];
-          s += li * tvec[m];
-        }
+#pragma unroll 8
+        for (int m = 0; m < NB; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
       }
     } else {
-      // ---- panel tile: L_ij = C Linv_jj^T ----------------------------------------------------
-      double* Cs = buf;            // [m][r] = C[r][m]
-      double* Bs = buf + NB * NB;  // [m][c] = Linv[c][m]
+      // ---- panel tile: L_ij = (A_ij - acc) Linv_jj^T -----------------------------------------
+      double* Cs = buf;                  // [m][r] = C[r][m]
+      double* Bs = buf + kTileDoubles;   // [m][c] = Linv[c][m]
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
+            Cs[c * LDT + r] = __ldcg(Aij + (size_t)c * ld + r) - acc.v[mi][ni][e];
+          }
       wait_flag(&g.flags[(size_t)j * T + j], epoch);
       __syncthreads();
-      {
-        const double* LT = g.LinvT + (size_t)j * NB * NB;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int chunk = it * kSolveThreads + tid;
-          cp_async16(Bs + chunk * 2, LT + chunk * 2);
-        }
-        cp_async_commit();
-      }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const double* colp = Aij + (size_t)(4 * tc + b) * ld + 4 * tr;
-        const double2 v0 = __ldcg(reinterpret_cast<const double2*>(colp));
-        const double2 v1 = __ldcg(reinterpret_cast<const double2*>(colp + 2));
-        double* d = Cs + (4 * tc + b) * NB + 4 * tr;
-        *reinterpret_cast<double2*>(d) = make_double2(v0.x - acc[0][b], v0.y - acc[1][b]);
-        *reinterpret_cast<double2*>(d + 2) = make_double2(v1.x - acc[2][b], v1.y - acc[3][b]);
-      }
+      BA_TRACE(t, 4);   // diagonal inverse available
+      stage_tile(Bs, g.LinvT + (size_t)j * NB * NB, NB);
+      cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
-      double out[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) out[a][b] = 0.0;
-      tile_mma(out, Cs, Bs, tr, tc);
+      Frag out;
+      out.zero();
+      tile_dmma(out, Cs, Bs, R0, C0, lane);
       double* Lij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        double* colp = Lij + (size_t)(4 * tc + b) * ld + 4 * tr;
-        *reinterpret_cast<double2*>(colp) = make_double2(out[0][b], out[1][b]);
-        *reinterpret_cast<double2*>(colp + 2) = make_double2(out[2][b], out[3][b]);
-      }
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
+            Lij[(size_t)c * ld + r] = out.v[mi][ni][e];
+          }
     }
     // ---- publish ------------------------------------------------------------------------------
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(&g.flags[(size_t)i * T + j], epoch);
+    BA_TRACE(t, 5);   // published
   }
 
   // ==================================== backward substitution ==============================
   // x_k = L_kk^{-T} (y_k - sum_{i>k} L_ik^T x_i),  k = T-1 .. 0
-  double* const part = buf;            // [8 warps][NB] partial sums
+  double* const part = buf;            // [4][NB] partial sums
   double* const accv = vec;            // [NB]
   double* const LTs = buf + 8 * NB;    // [NB][NBP] padded copy of LinvT
-  const int lane = tid & 31, wid = tid >> 5;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_task = (int)atomicAdd(&g.tickets[1], 1u);
@@ -367,6 +434,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     const int bt = s_task;
     if (bt >= T) break;
     const int k = T - 1 - bt;
+    BA_TRACE_SET(ntasks + bt, 0, (unsigned long long)k);
+    BA_TRACE_SET(ntasks + bt, 1, (unsigned long long)blockIdx.x);
+    BA_TRACE(ntasks + bt, 2);
     wait_flag(&g.flags[(size_t)k * T + k], epoch);   // L_kk^{-1} and y_k
     __syncthreads();
     {
@@ -387,6 +457,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       for (int q = 0; q < 8; ++q)
         cs[q] += __ldcg(Lik + (size_t)q * ld + lane) * x0 + __ldcg(Lik + (size_t)q * ld + 32 + lane) * x1;
     }
+    BA_TRACE(ntasks + bt, 3);   // all x_i folded
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const double s = warp_sum(cs[q]);
@@ -408,6 +479,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(&g.flags[(size_t)T * T + k], epoch);
+    BA_TRACE(ntasks + bt, 5);
   }
 }
 
@@ -435,6 +507,9 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   g.status = &c.scalars->status;
   g.ld = ld; g.T = T;
   g.epoch = ++c.solve_epoch;   // a fresh epoch per call: flags never need clearing
+#ifdef BA_SOLVE_TRACE
+  g.trace = c.solve_trace;
+#endif
   const int ntasks = T * (T + 1) / 2;
   int grid = ntasks < c.num_sms ? ntasks : c.num_sms;   // 1 CTA / SM (128 KB smem): all co-resident
   chol_dataflow_kernel<<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
