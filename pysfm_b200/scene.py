@@ -126,6 +126,36 @@ def pack_scene(bundle, camera_ids, track_ids, optim_camera_indices, optim_track_
     return s
 
 
+def packed_system_index(n_opt_cam):
+    """(rows, cols) of the dense reduced-system entry stored at every slot of the packed block
+    triangle (include/ba_b200.h): 6x6 blocks (a, b), a <= b, block rows back to back, 36
+    row-major doubles each."""
+    a, b = np.triu_indices(n_opt_cam)
+    rows = (6 * a)[:, None, None] + np.arange(6)[None, :, None] + np.zeros((1, 1, 6), dtype=np.int64)
+    cols = (6 * b)[:, None, None] + np.arange(6)[None, None, :] + np.zeros((1, 6, 1), dtype=np.int64)
+    return rows.reshape(-1), cols.reshape(-1)
+
+
+def pack_system(A, b):
+    """Dense symmetric A (n, n) and b (n,) -> the packed buffer [upper blocks || b]."""
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    n = b.size
+    A = np.asarray(A, dtype=np.float64).reshape(n, n)
+    rows, cols = packed_system_index(n // 6)
+    return np.concatenate((A[rows, cols], b))
+
+
+def unpack_system(packed, n_opt_cam):
+    """Inverse of pack_system: (A, b) with A mirrored from the stored upper block triangle."""
+    n = 6 * n_opt_cam
+    packed = np.asarray(packed, dtype=np.float64)
+    rows, cols = packed_system_index(n_opt_cam)
+    A = np.zeros((n, n))
+    A[cols, rows] = packed[:rows.size]
+    A[rows, cols] = packed[:rows.size]      # diagonal blocks are stored in full: keep as written
+    return A, packed[rows.size:rows.size + n].copy()
+
+
 def _as_vp(t):
     return ctypes.c_void_p(t.data_ptr())
 
@@ -267,23 +297,12 @@ class DeviceProblem(object):
         assert a.shape == (self.scene.n_opt_cam, 6), 'shape was ' + str(a.shape)
         self._chk(self.lib.ba_set_solution(self.h, a.ctypes.data_as(ctypes.c_void_p), self._stream()), "ba_set_solution")
 
-    def _packed_index(self):
-        """(rows, cols) of the dense matrix entry stored at every slot of the packed block
-        triangle (include/ba_b200.h): blocks (a, b), a <= b, row by row, 36 doubles each."""
-        nc = self.scene.n_opt_cam
-        a, b = np.triu_indices(nc)
-        rows = (6 * a)[:, None, None] + np.arange(6)[None, :, None] + np.zeros((1, 1, 6), dtype=np.int64)
-        cols = (6 * b)[:, None, None] + np.arange(6)[None, None, :] + np.zeros((1, 6, 1), dtype=np.int64)
-        return rows.reshape(-1), cols.reshape(-1)
-
     def upload_system(self, A, b):
         """Overwrite the bound reduced system with a caller-supplied dense symmetric A and b."""
         n = self.n_sys
         A = np.asarray(A, dtype=np.float64).reshape(n, n)
-        rows, cols = self._packed_index()
         host = np.zeros(max(self.sys_len, 2))
-        host[:rows.size] = A[rows, cols]
-        host[rows.size:rows.size + n] = np.asarray(b, dtype=np.float64).reshape(n)
+        host[:self.sys_len] = pack_system(A, b)
         self.sys.copy_(self.torch.as_tensor(host))
 
     def copy_solution_to(self, out_dC, out_dP):
@@ -323,13 +342,7 @@ class DeviceProblem(object):
 
     def system(self):
         """(A, b): A = dense symmetric (n_sys, n_sys) rebuilt from the packed upper blocks."""
-        n = self.n_sys
-        host = self.sys.cpu().numpy()
-        rows, cols = self._packed_index()
-        A = np.zeros((n, n))
-        A[cols, rows] = host[:rows.size]
-        A[rows, cols] = host[:rows.size]      # diagonal blocks are stored in full: keep as written
-        return A, host[rows.size:rows.size + n].copy()
+        return unpack_system(self.sys.cpu().numpy()[:self.sys_len], self.scene.n_opt_cam)
 
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))
