@@ -83,17 +83,51 @@ struct ElimArgs {
   double* __restrict__ cost_out;
 };
 
-// per-observation shared-memory record (doubles): Jc 12 | W 18 | Y 18 | jtr 6 | slot(1)
+// Per-warp shared memory (doubles):
+//   stage [32][kStageStride]   one 6x6 block per lane, source of the bulk reductions
+//   Jc [kcap][12] | Wv [kcap][18] | Yv [kcap][18] | jtr [kcap][6] | sb [kcap] (int2 {slot, row base})
+// Strides are chosen so that the 128-bit accesses of a quarter-warp fall into distinct banks:
+// 18 doubles = 9 x 16 B per W/Y record, 38 doubles = 19 x 16 B per staged block.
+constexpr int kStageStride = 38;
+constexpr int kStageDoubles = 32 * kStageStride;
 constexpr int kObsRec = 12 + 18 + 18 + 6 + 1;
+__host__ __device__ __forceinline__ int elim_warp_doubles(int kcap) {
+  return (kStageDoubles + kObsRec * kcap + 1) & ~1;
+}
+
+// q-th pair (a <= b) of a point with k observations, rows a = 0..k-1 holding b = a..k-1
+__device__ __forceinline__ void pair_from_index(int q, int k, int& a, int& b) {
+  const float kk = 2.f * (float)k + 1.f;
+  int aa = (int)((kk - sqrtf(fmaxf(kk * kk - 8.f * (float)q, 0.f))) * 0.5f);
+  aa = aa < 0 ? 0 : (aa > k - 1 ? k - 1 : aa);
+  while (aa > 0 && aa * k - aa * (aa - 1) / 2 > q) --aa;
+  while ((aa + 1) * k - (aa + 1) * aa / 2 <= q) ++aa;
+  a = aa;
+  b = aa + (q - (aa * k - aa * (aa - 1) / 2));
+}
+
+// S[dst .. dst+36) += stage[0 .. 36)  as ONE asynchronous bulk reduction (TMA path, SASS UBLKRED):
+// the 99 M FP64 additions of a config-2 iteration reach L2 without occupying the LSU pipe.
+__device__ __forceinline__ void bulk_add_block(double* dst, const double* src_smem) {
+  const unsigned int src = (unsigned int)__cvta_generic_to_shared(src_smem);
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 288;"
+               ::"l"(dst), "r"(src) : "memory");
+}
 
 template <bool WANT_BLOCKS, bool WANT_SCHUR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 linearize_eliminate_kernel(const ElimArgs A) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  double* rec = smem + (size_t)wid * A.kcap * kObsRec;
+  double* const stage = smem + (size_t)wid * elim_warp_doubles(A.kcap);
+  double* const Jcs = stage + kStageDoubles;
+  double* const Wv = Jcs + 12 * A.kcap;
+  double* const Yv = Wv + 18 * A.kcap;
+  double* const jtrs = Yv + 18 * A.kcap;
+  int2* const sbs = reinterpret_cast<int2*>(jtrs + 6 * A.kcap);
+  double* const my_stage = stage + lane * kStageStride;
   const ObsArgs& o = A.o;
   const double damp1 = 1.0 + A.damping;
   double* __restrict__ S = A.sys;
@@ -125,25 +159,25 @@ linearize_eliminate_kernel(const ElimArgs A) {
       bl[1] += Jp[1] * r[0] + Jp[4] * r[1];
       bl[2] += Jp[2] * r[0] + Jp[5] * r[1];
       if (slot >= 0 && pt_free) cost_acc += r[0] * r[0] + r[1] * r[1];
-      double* q = rec + (size_t)a * kObsRec;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) q[i] = Jc[i];
+      for (int i = 0; i < 12; i += 2)
+        *reinterpret_cast<double2*>(Jcs + a * 12 + i) = make_double2(Jc[i], Jc[i + 1]);
       double Wl[18];
 #pragma unroll
       for (int rr = 0; rr < 6; ++rr)
 #pragma unroll
         for (int m = 0; m < 3; ++m) Wl[rr * 3 + m] = Jc[rr] * Jp[m] + Jc[6 + rr] * Jp[3 + m];
 #pragma unroll
-      for (int i = 0; i < 18; ++i) q[12 + i] = Wl[i];
+      for (int i = 0; i < 18; i += 2)
+        *reinterpret_cast<double2*>(Wv + a * 18 + i) = make_double2(Wl[i], Wl[i + 1]);
       double jtr[6];
 #pragma unroll
-      for (int rr = 0; rr < 6; ++rr) {
-        jtr[rr] = Jc[rr] * r[0] + Jc[6 + rr] * r[1];
-        q[48 + rr] = jtr[rr];
-      }
+      for (int rr = 0; rr < 6; ++rr) jtr[rr] = Jc[rr] * r[0] + Jc[6 + rr] * r[1];
+#pragma unroll
+      for (int i = 0; i < 6; i += 2)
+        *reinterpret_cast<double2*>(jtrs + a * 6 + i) = make_double2(jtr[i], jtr[i + 1]);
       // packed row base: block (slot, b) lives at index rowbase + b, b >= slot
-      reinterpret_cast<int2*>(q + 54)[0] =
-          make_int2(slot, slot >= 0 ? slot * A.n_opt_cam - slot * (slot - 1) / 2 - slot : 0);
+      sbs[a] = make_int2(slot, slot >= 0 ? slot * A.n_opt_cam - slot * (slot - 1) / 2 - slot : 0);
       if (WANT_BLOCKS) {
         double* Uc = A.U + (size_t)cam * 36;
 #pragma unroll
@@ -183,58 +217,74 @@ linearize_eliminate_kernel(const ElimArgs A) {
     // ---- phase C: Y = W Vinv rows, reduced right-hand side -------------------------------
     for (int task = lane; task < 6 * k; task += 32) {
       const int a = task / 6, rr = task - 6 * a;
-      double* q = rec + (size_t)a * kObsRec;
-      const double w0 = q[12 + rr * 3], w1 = q[12 + rr * 3 + 1], w2 = q[12 + rr * 3 + 2];
+      const double w0 = Wv[a * 18 + rr * 3], w1 = Wv[a * 18 + rr * 3 + 1], w2 = Wv[a * 18 + rr * 3 + 2];
       const double y0 = w0 * Vi[0] + w1 * Vi[3] + w2 * Vi[6];
       const double y1 = w0 * Vi[1] + w1 * Vi[4] + w2 * Vi[7];
       const double y2 = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
-      q[30 + rr * 3] = y0; q[30 + rr * 3 + 1] = y1; q[30 + rr * 3 + 2] = y2;
-      const int slot = reinterpret_cast<const int*>(q + 54)[0];
+      Yv[a * 18 + rr * 3] = y0; Yv[a * 18 + rr * 3 + 1] = y1; Yv[a * 18 + rr * 3 + 2] = y2;
+      const int slot = sbs[a].x;
       if (slot >= 0)
-        atomicAdd(rhs + 6 * slot + rr, q[48 + rr] - (y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
+        atomicAdd(rhs + 6 * slot + rr, jtrs[a * 6 + rr] - (y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
     }
     __syncwarp();
-    // ---- phase D1: diagonal blocks  S_aa += damped Jc^T Jc - Y_a W_a^T ---------------------
-    // lanes span the 36 contiguous entries of each free camera's diagonal block
-    for (int task = lane; task < 36 * k; task += 32) {
-      const int a = task / 36, e = task - 36 * a;
-      const int rr = e / 6, cc = e - 6 * rr;
-      const double* q = rec + (size_t)a * kObsRec;
-      const int2 sb = reinterpret_cast<const int2*>(q + 54)[0];   // {slot, packed row base}
-      if (sb.x < 0) continue;
-      double d = q[rr] * q[cc] + q[6 + rr] * q[6 + cc];
-      if (rr == cc) d *= damp1;
-      d -= q[30 + rr * 3] * q[12 + cc * 3] + q[30 + rr * 3 + 1] * q[12 + cc * 3 + 1] +
-           q[30 + rr * 3 + 2] * q[12 + cc * 3 + 2];
-      atomicAdd(S + ((size_t)(sb.y + sb.x) * 36 + e), d);
-    }
-    // ---- phase D2: off-diagonal blocks  S_ab -= Y_a W_b^T, a < b (slots ascend inside a
-    // point, so (a, b) is always in the stored upper block triangle) -------------------------
-    for (int s0 = 6; s0 < 6 * k; s0 += 32) {   // b = 0 has no partner a < b
-      const int s = s0 + lane;
-      bool valid = s < 6 * k;
-      const int b = valid ? s / 6 : 0;
-      const int cc = valid ? s - 6 * b : 0;
-      const double* qb = rec + (size_t)b * kObsRec;
-      const double wb0 = qb[12 + cc * 3], wb1 = qb[12 + cc * 3 + 1], wb2 = qb[12 + cc * 3 + 2];
-      const int slot_b = reinterpret_cast<const int*>(qb + 54)[0];
-      valid = valid && slot_b >= 0;
-      const int amax = min(k - 1, (s0 + 31) / 6);   // exclusive bound is b, checked per lane
-      for (int a = 0; a < amax; ++a) {
-        const double* qa = rec + (size_t)a * kObsRec;
-        const int2 sa = reinterpret_cast<const int2*>(qa + 54)[0];
-        if (sa.x < 0) continue;  // warp-uniform
-        if (valid && a < b) {
-          double* dst = S + ((size_t)(sa.y + slot_b) * 36 + cc);
+    // ---- phase D: one lane per camera pair (a <= b) of the point.  The lane forms the whole 6x6
+    // block in registers ( -Y_a W_b^T, plus the damped Jc^T Jc on the diagonal pairs), parks it
+    // in its staging slot and hands it to the bulk-reduction engine.  Slots ascend inside a
+    // point, so (a, b) is always in the stored upper block triangle. --------------------------
+    // Pair order: the k diagonal pairs (a, a) first, then the k(k-1)/2 pairs a < b row by row,
+    // so that only the first round(s) carry the Jc^T Jc term.
+    const int npairs = k * (k + 1) / 2;
+    for (int q0 = 0; q0 < npairs; q0 += 32) {
+      const int q = q0 + lane;
+      // the previous round's (or point's) reduction must have finished READING this slot
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (q < npairs) {
+        int a, b;
+        if (q < k) {
+          a = b = q;
+        } else {
+          pair_from_index(q - k, k - 1, a, b);
+          b += 1;
+        }
+        const int2 sa = sbs[a];
+        if (sa.x >= 0) {
+          const int slot_b = sbs[b].x;
+          double Wb[18];
 #pragma unroll
-          for (int rr = 0; rr < 6; ++rr)
-            atomicAdd(dst + rr * 6,
-                      -(qa[30 + rr * 3] * wb0 + qa[30 + rr * 3 + 1] * wb1 + qa[30 + rr * 3 + 2] * wb2));
+          for (int i = 0; i < 18; i += 2) {
+            const double2 w = *reinterpret_cast<const double2*>(Wv + b * 18 + i);
+            Wb[i] = w.x; Wb[i + 1] = w.y;
+          }
+          const double* Ya = Yv + a * 18;
+          const double* Jca = Jcs + a * 12;
+#pragma unroll
+          for (int rr = 0; rr < 6; ++rr) {
+            const double y0 = Ya[rr * 3], y1 = Ya[rr * 3 + 1], y2 = Ya[rr * 3 + 2];
+            double v[6];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc)
+              v[cc] = -(y0 * Wb[cc * 3] + y1 * Wb[cc * 3 + 1] + y2 * Wb[cc * 3 + 2]);
+            if (q0 < k && a == b) {   // diagonal pair: + damped Jc^T Jc
+              const double j0 = Jca[rr], j1 = Jca[6 + rr];
+#pragma unroll
+              for (int cc = 0; cc < 6; ++cc) {
+                const double d = j0 * Jca[cc] + j1 * Jca[6 + cc];
+                v[cc] += (rr == cc) ? d * damp1 : d;
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 6; cc += 2)
+              *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
         }
       }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     __syncwarp();
   }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
 }
 
@@ -286,22 +336,42 @@ struct BacksubArgs {
   double* __restrict__ cost_out;
 };
 
-__global__ void __launch_bounds__(256) backsub_cost_kernel(const BacksubArgs A) {
+// sum over the G-lane group a lane belongs to (G = 8, 16 or 32, groups are lane-aligned)
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// G lanes per point: with tracks of <= 16 (<= 8) observations a warp works on 2 (4) points at a
+// time, which halves (quarters) the number of dependent load -> compute -> reduce round trips
+// each warp goes through; this kernel is bound by that latency chain, not by bytes.
+template <int G>
+__global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs A) {
   const ObsArgs& o = A.o;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
+  constexpr int NG = 32 / G;
+  const int sub = lane / G, gl = lane % G;
   double cost_acc = 0.0;
-  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
-    const int beg = o.pt_ptr[pt];
-    const int k = o.pt_ptr[pt + 1] - beg;
-    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
-    const int pslot = o.pt_slot[pt];
+  for (int base = (blockIdx.x * warps_per_cta + wid) * NG; base < o.n_pt; base += gridDim.x * warps_per_cta * NG) {
+    const int pt = base + sub;
+    const bool live = pt < o.n_pt;
+    const int beg = live ? o.pt_ptr[pt] : 0;
+    const int k = live ? o.pt_ptr[pt + 1] - beg : 0;
+    double x[3] = {0.0, 0.0, 0.0};
+    int pslot = -1;
+    if (live) {
+      x[0] = o.pts[3 * pt]; x[1] = o.pts[3 * pt + 1]; x[2] = o.pts[3 * pt + 2];
+      pslot = o.pt_slot[pt];
+    }
     double xc[3] = {x[0], x[1], x[2]};
+    // sum_j W_j^T dC_j  ==  sum_j Jp_j^T (Jc_j dC_j)
+    double acc[3] = {0, 0, 0};
     if (pslot >= 0) {
-      // sum_j W_j^T dC_j  ==  sum_j Jp_j^T (Jc_j dC_j)
-      double acc[3] = {0, 0, 0};
-      for (int a = lane; a < k; a += 32) {
+      for (int a = gl; a < k; a += G) {
         const int ob = beg + a;
         const int cam = o.obs_cam[ob];
         const int slot = o.cam_slot[cam];
@@ -316,8 +386,10 @@ __global__ void __launch_bounds__(256) backsub_cost_kernel(const BacksubArgs A) 
 #pragma unroll
         for (int m = 0; m < 3; ++m) acc[m] += Jp[m] * q0 + Jp[3 + m] * q1;
       }
+    }
 #pragma unroll
-      for (int m = 0; m < 3; ++m) acc[m] = warp_sum(acc[m]);
+    for (int m = 0; m < 3; ++m) acc[m] = group_sum<G>(acc[m]);
+    if (pslot >= 0) {
       const double g0 = A.bP[3 * pt] - acc[0], g1 = A.bP[3 * pt + 1] - acc[1], g2 = A.bP[3 * pt + 2] - acc[2];
       const double* Vi = A.Vinv + (size_t)pt * 9;
       double dp[3];
@@ -325,20 +397,20 @@ __global__ void __launch_bounds__(256) backsub_cost_kernel(const BacksubArgs A) 
       for (int m = 0; m < 3; ++m) dp[m] = Vi[3 * m] * g0 + Vi[3 * m + 1] * g1 + Vi[3 * m + 2] * g2;
 #pragma unroll
       for (int m = 0; m < 3; ++m) xc[m] = x[m] - dp[m];
-      if (lane == 0) {
+      if (gl == 0) {
 #pragma unroll
         for (int m = 0; m < 3; ++m) A.dP[3 * pt + m] = dp[m];
       }
-    } else if (lane == 0) {
+    } else if (live && gl == 0) {
 #pragma unroll
       for (int m = 0; m < 3; ++m) A.dP[3 * pt + m] = 0.0;
     }
-    if (lane == 0) {
+    if (live && gl == 0) {
 #pragma unroll
       for (int m = 0; m < 3; ++m) A.cand_pts[3 * pt + m] = xc[m];
     }
     if (pslot >= 0) {
-      for (int a = lane; a < k; a += 32) {
+      for (int a = gl; a < k; a += G) {
         const int ob = beg + a;
         const int cam = o.obs_cam[ob];
         if (o.cam_slot[cam] < 0) continue;
@@ -458,13 +530,13 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   A.kcap = kcap;
   A.sys = c.sys; A.Vinv = c.Vinv; A.bP = c.bP; A.V = c.V; A.U = c.U; A.bC = c.bC; A.W = c.W;
   A.partials = c.partials; A.ticket = c.counters; A.cost_out = &c.scalars->cost;
-  const size_t per_warp = (size_t)kcap * kObsRec * sizeof(double);
+  const size_t per_warp = (size_t)elim_warp_doubles(kcap) * sizeof(double);
   const size_t budget = 200 * 1024;
   int warps = (int)(budget / per_warp);
   if (warps < 1) return cudaErrorInvalidValue;  // track too long for the shared-memory tile
   if (warps > 8) warps = 8;
   const size_t smem = per_warp * warps;
-  int ctas_per_sm = (int)(budget / smem);
+  int ctas_per_sm = (int)((budget + 24 * 1024) / (smem + 1024));
   if (ctas_per_sm > 8 / warps * 4) ctas_per_sm = 8 / warps * 4;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int grid = point_grid(c, warps, ctas_per_sm);
@@ -492,8 +564,15 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   A.cand_R = c.cand.cam_R; A.cand_t = c.cand.cam_t; A.cand_pts = c.cand.pts;
   A.dC = c.dC; A.Vinv = c.Vinv; A.bP = c.bP; A.dP = c.dP;
   A.partials = c.partials; A.ticket = c.counters + 1; A.cost_out = &c.scalars->cand_cost;
-  const int grid = point_grid(c, 8, 8);
-  backsub_cost_kernel<<<grid, 256, 0, st>>>(A);
+  // lanes per point: the narrowest group that still holds the longest track in one pass
+  const int kmax = c.max_track_len < 1 ? 32 : c.max_track_len;
+  if (kmax <= 8) {
+    backsub_cost_kernel<8><<<point_grid(c, 8 * 4, 3), 256, 0, st>>>(A);
+  } else if (kmax <= 16) {
+    backsub_cost_kernel<16><<<point_grid(c, 8 * 2, 3), 256, 0, st>>>(A);
+  } else {
+    backsub_cost_kernel<32><<<point_grid(c, 8, 3), 256, 0, st>>>(A);
+  }
   c.launches += 1;
   return cudaGetLastError();
 }

@@ -117,7 +117,7 @@ struct CholArgs {
   double* __restrict__ rhs;       // [ld] b -> y (forward substitution)
   double* __restrict__ x;         // [ld] solution
   double* __restrict__ LinvT;     // [T][NB*NB]  LinvT[m*NB + c] = (L_jj^{-1})[c][m]
-  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready
+  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready
   unsigned int* __restrict__ tickets; // [0] tile tasks, [1] back-substitution tasks
   double* __restrict__ status;    // set to 1 on a non-positive pivot
   int ld, T;
@@ -161,8 +161,15 @@ struct Frag {
   }
 };
 
-// acc += P^T Q over the 64-long contraction:  acc[r][c] += sum_m P[m*LDT + r] * Q[m*LDT + c]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// acc (+/-)= P^T Q over the 64-long contraction:  acc[r][c] += sum_m P[m*LDT + r] * Q[m*LDT + c]
 // (FP64 tensor-core path: mma.sync.m8n8k4.f64, SASS DMMA.8x8x4)
+template <bool NEG>
 __device__ __forceinline__ void tile_dmma(Frag& acc, const double* __restrict__ P,
                                           const double* __restrict__ Q, int R0, int C0, int lane) {
   const int g = lane >> 2, t4 = lane & 3;
@@ -172,26 +179,66 @@ __device__ __forceinline__ void tile_dmma(Frag& acc, const double* __restrict__ 
   for (int m0 = 0; m0 < NB; m0 += 4) {
     double a[4], b[2];
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) a[mi] = pa[m0 * LDT + 8 * mi];
+    for (int mi = 0; mi < 4; ++mi) a[mi] = NEG ? -pa[m0 * LDT + 8 * mi] : pa[m0 * LDT + 8 * mi];
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) b[ni] = pb[m0 * LDT + 8 * ni];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni)
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(acc.v[mi][ni][0]), "+d"(acc.v[mi][ni][1])
-                     : "d"(a[mi]), "d"(b[ni]));
+      for (int ni = 0; ni < 2; ++ni) dmma884(acc.v[mi][ni][0], acc.v[mi][ni][1], a[mi], b[ni]);
   }
 }
+
+// Diagonal tasks keep the lower triangle of their tile as 8x8 DMMA accumulator tiles owned by
+// ROW BLOCK: warp r holds tiles (r, c), c <= r;  t[c][e] <-> row 8r + (lane >> 2), column
+// 8c + 2 (lane & 3) + e.  The blocked sweep below updates them in place.
+struct RowTiles {
+  double t[8][2];
+};
+
+// W(r, c) -= sum_m P[m*LDT + 8r + .] * P[m*LDT + 8c + .],  c <= r
+__device__ __forceinline__ void diag_rows_dmma(RowTiles& W, const double* __restrict__ P, int r, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* p = P + t4 * LDT + g;
+#pragma unroll 2
+  for (int m0 = 0; m0 < NB; m0 += 4) {
+    const double* pm = p + m0 * LDT;
+    const double a = -pm[8 * r];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c <= r) dmma884(W.t[c][0], W.t[c][1], a, pm[8 * c]);
+  }
+}
+
+// 1/d for a pivot d > 0: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) and one third-order
+// Newton step (3 dependent DFMA) -> ~2^-60 relative error, without the special-case branches
+// and the two extra DFMAs of the IEEE division that sat on the pivot chain.
+__device__ __forceinline__ double pivot_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  return fma(x, e, x);
+}
+
+// v[t4] of a 4-vector held in registers, without dynamic register indexing
+__device__ __forceinline__ double sel4(double v0, double v1, double v2, double v3, int t4) {
+  const double lo = (t4 & 1) ? v1 : v0, hi = (t4 & 1) ? v3 : v2;
+  return (t4 & 2) ? hi : lo;
+}
+
+// 8x8 scratch tiles of the blocked sweep: row stride 12 doubles (conflict-free fragment loads)
+constexpr int TS = 12;
+constexpr int TD = 8 * TS;
 
 // Shared memory map (doubles):
 //   buf[4][NB*LDT]     double-buffered operand tiles (P, Q) of the k loop           136 KB
 //   aliases used after the k loop of a task:
-//     LTs = buf                diagonal task: scaled L_jj^{-1}, transposed, [m][c]
+//     LTs  = buf               diagonal task: L_jj^{-1}, transposed, [m][c]
+//     Wcol, Mrow, Lp, Mp = buf + NB*LDT ...   diagonal task: 8x8 scratch tiles of the sweep
 //     Cs  = buf                panel task: C transposed to [m][r]
 //     Bs  = buf + NB*LDT       panel task: LinvT tile [m][c]
-//   vec[8][NB]  u[2], um[2] (pivot rows of W and M, ping-pong), piv, isd, tvec, yk
+//   vec[8][NB]  accv (backward phase), tvec, yk
 constexpr int kSolveSmemDoubles = 4 * kTileDoubles + 8 * NB;
 constexpr size_t kSolveSmemBytes = kSolveSmemDoubles * sizeof(double);
 
@@ -199,10 +246,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   extern __shared__ __align__(16) double sm[];
   double* const buf = sm;
   double* const vec = sm + 4 * kTileDoubles;
-  double* const u_buf = vec;             // [2][NB]
-  double* const um_buf = vec + 2 * NB;   // [2][NB]
-  double* const piv = vec + 4 * NB;
-  double* const isd = vec + 5 * NB;
   double* const tvec = vec + 6 * NB;
   double* const yk = vec + 7 * NB;
   __shared__ int s_task;
@@ -240,149 +283,231 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     BA_TRACE_SET(t, 1, (unsigned long long)blockIdx.x);
     BA_TRACE(t, 2);   // task grabbed
 
-    Frag acc;
-    acc.zero();
-    double bacc = 0.0;  // diag task, tid < NB: sum_k (L_jk y_k)[tid]
-
-    // ---- k loop: acc += L_ik L_jk^T, operands double-buffered through cp.async ------------
-    auto issue = [&](int k) {
-      double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
-      stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)i * NB, ld);
-      if (!diag) stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
-      cp_async_commit();
-    };
-    if (j > 0) {
-      wait_flag(&g.flags[(size_t)i * T + 0], epoch);
-      if (!diag) wait_flag(&g.flags[(size_t)j * T + 0], epoch);
-      __syncthreads();
-      issue(0);
-    }
-    for (int k = 0; k < j; ++k) {
-      if (k + 1 < j) {
-        wait_flag(&g.flags[(size_t)i * T + k + 1], epoch);
-        if (!diag) wait_flag(&g.flags[(size_t)j * T + k + 1], epoch);
-        __syncthreads();
-        issue(k + 1);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      if (diag && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
-      __syncthreads();
-      const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
-      const double* Q = diag ? P : P + kTileDoubles;
-      tile_dmma(acc, P, Q, R0, C0, lane);
-      if (diag && tid < NB) {
-        double s = 0.0;
-#pragma unroll 8
-        for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
-        bacc += s;
-      }
-      __syncthreads();
-    }
-    BA_TRACE(t, 3);   // k loop done
-
     const double* Aij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
+    unsigned int* const yflag = g.flags + (size_t)T * T + T;
+
     if (diag) {
-      // ---- W = A_jj - acc (full symmetric tile: only the lower triangle is valid in memory),
-      //      M = I;  both live in registers in the DMMA layout -------------------------------
-      Frag W, M;
+      // ================================ diagonal task ==========================================
+      // W = A_jj - sum_k L_jk L_jk^T, lower triangle only, as row-block-owned 8x8 tiles.  The
+      // original A_jj is fetched first so that its latency hides behind the k loop.
+      const int r = wid;
+      RowTiles W;
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+      for (int c = 0; c < 8; ++c)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
+        for (int e = 0; e < 2; ++e) {
+          const int row = 8 * r + gq, col = 8 * c + 2 * t4 + e;
+          const int hi = row > col ? row : col, lo = row > col ? col : row;
+          W.t[c][e] = (c <= r) ? __ldcg(Aij + (size_t)lo * ld + hi) : 0.0;
+        }
+      double bacc = 0.0;  // tid < NB: sum_k (L_jk y_k)[tid]
+      const double rhs_j = (tid < NB) ? __ldcg(g.rhs + j * NB + tid) : 0.0;   // b_j, fetched early
+      double* const LT = g.LinvT + (size_t)j * NB * NB;
+      auto issue = [&](int k) {
+        stage_tile(buf + (size_t)(2 * (k & 1)) * kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
+        cp_async_commit();
+      };
+      if (j > 0) {
+        wait_flag(&g.flags[(size_t)j * T + 0], epoch);
+        wait_flag(&yflag[0], epoch);
+        __syncthreads();
+        issue(0);
+      }
+      for (int k = 0; k < j; ++k) {
+        if (k + 1 < j) {
+          wait_flag(&g.flags[(size_t)j * T + k + 1], epoch);
+          wait_flag(&yflag[k + 1], epoch);
+          __syncthreads();
+          issue(k + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        if (tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
+        __syncthreads();
+        const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+        diag_rows_dmma(W, P, r, lane);
+        if (tid < NB) {
+          double s = 0.0;
+#pragma unroll 8
+          for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
+          bacc += s;
+        }
+        __syncthreads();
+      }
+      BA_TRACE(t, 3);   // k loop done
+
+      // ---- blocked sweep: 8 panel steps of 8 pivots.  Step pb: every warp r >= pb factors the
+      // 8x8 pivot block D redundantly (Gauss-Jordan in registers, one row per lane quad) into
+      // Linv_d = L_d^{-1};  warp r > pb forms its panel tile Lp_r = W(r,pb) Linv_d^T, warp pb
+      // the finished row block of the inverse  Mp_c = Linv_d M(pb,c);  after one barrier the
+      // trailing tiles take the rank-8 update  W(r,c) -= Lp_r Lp_c^T,  M(r,c) -= Lp_r Mp_c
+      // on the FP64 tensor pipe.  M accumulates L~^{-1} exactly as in a Gauss-Jordan sweep of
+      // [W | I], so the row blocks Mp are the rows of L_jj^{-1}; L_jj itself is never needed.
+      double* const LTs = buf;                          // [m][c'] = Linv[c'][m], row stride LDT
+      double* const Wcol = buf + kTileDoubles;          // [8][TD]  column block pb of W
+      double* const Mrow = Wcol + 8 * TD;               // [8][TD]  row block pb of M
+      double* const Lp = Mrow + 8 * TD;                 // [8][TD]  panel tiles
+      double* const Mp = Lp + 8 * TD;                   // [8][TD]  row block pb of Linv
+      RowTiles M;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            const int hi = r > c ? r : c, lo = r > c ? c : r;
-            W.v[mi][ni][e] = __ldcg(Aij + (size_t)lo * ld + hi) - acc.v[mi][ni][e];
-            M.v[mi][ni][e] = (r == c) ? 1.0 : 0.0;
-          }
+      for (int c = 0; c < 8; ++c) M.t[c][0] = M.t[c][1] = 0.0;
+      for (int e = tid; e < NB * LDT; e += kSolveThreads) LTs[e] = 0.0;
       if (tid == 0) s_bad = 0;
-      // Gauss-Jordan sweep without pivoting.  After step p the rows r > p of W hold the Schur
-      // complement (kept symmetric, so column p equals row p) and M accumulates the unit
-      // lower-triangular L~^{-1}:  M A = U = D L~^T.  One barrier per step: the owners of row
-      // p+1 publish it (ping-pong buffers) right after their update of step p.
-      auto publish_row = [&](int p) {
-        double* u = u_buf + (p & 1) * NB;
-        double* um = um_buf + (p & 1) * NB;
+      *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[0][0], W.t[0][1]);
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-          if (R0 + 8 * mi + gq == p) {
+      for (int pb = 0; pb < 8; ++pb) {
+        __syncthreads();   // (A) Wcol tiles r >= pb and Mrow tiles c < pb are in place
+        if (r >= pb) {
+          double w[8], m[8];
+          {
+            const double* drow = Wcol + pb * TD + gq * TS;
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) {
-              const int c = C0 + 8 * ni + 2 * t4;
-              *reinterpret_cast<double2*>(u + c) = make_double2(W.v[mi][ni][0], W.v[mi][ni][1]);
-              *reinterpret_cast<double2*>(um + c) = make_double2(M.v[mi][ni][0], M.v[mi][ni][1]);
+            for (int c = 0; c < 8; c += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(drow + c);
+              w[c] = v.x; w[c + 1] = v.y;
             }
           }
-      };
-      publish_row(0);
-      for (int p = 0; p < NB; ++p) {
-        __syncthreads();
-        const double* u = u_buf + (p & 1) * NB;
-        const double* um = um_buf + (p & 1) * NB;
-        double d = u[p];
-        if (!(d > 0.0)) {          // also catches NaN; uniform across the block
-          if (tid == 0) s_bad = 1;
-          d = 1.0;
-        }
-        if (tid == 0) piv[p] = d;
-        const double id = 1.0 / d;
-        double f[4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-          const int r = R0 + 8 * mi + gq;
-          f[mi] = (r > p) ? u[r] * id : 0.0;
-        }
+          for (int c = 0; c < 8; ++c) m[c] = (c == gq) ? 1.0 : 0.0;
+          double dmine = 1.0;
+          bool bad = false;
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni) {
-          const int c = C0 + 8 * ni + 2 * t4;
-          const double2 uc = *reinterpret_cast<const double2*>(u + c);
-          const double2 mc = *reinterpret_cast<const double2*>(um + c);
+          for (int p = 0; p < 8; ++p) {
+            double d = __shfl_sync(0xffffffffu, w[p], 4 * p);
+            if (!(d >= 1e-290)) { bad = true; d = 1.0; }  // also catches NaN; warp-uniform
+            if (gq == p) dmine = d;
+            double u[8], um[8];
 #pragma unroll
-          for (int mi = 0; mi < 4; ++mi) {
-            W.v[mi][ni][0] -= f[mi] * uc.x;
-            W.v[mi][ni][1] -= f[mi] * uc.y;
-            M.v[mi][ni][0] -= f[mi] * mc.x;
-            M.v[mi][ni][1] -= f[mi] * mc.y;
+            for (int c = p + 1; c < 8; ++c) u[c] = __shfl_sync(0xffffffffu, w[c], 4 * p);
+#pragma unroll
+            for (int c = 0; c < p; ++c) um[c] = __shfl_sync(0xffffffffu, m[c], 4 * p);
+            const double f = ((gq > p) ? w[p] : 0.0) * pivot_rcp(d);
+#pragma unroll
+            for (int c = p + 1; c < 8; ++c) w[c] -= f * u[c];
+#pragma unroll
+            for (int c = 0; c < p; ++c) m[c] -= f * um[c];
+            m[p] -= f;
+          }
+          if (bad && lane == 0) s_bad = 1;
+          const double isd = rsqrt(dmine);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m[c] *= isd;        // row gq of Linv_d
+          const double l0 = sel4(m[0], m[1], m[2], m[3], t4), l1 = sel4(m[4], m[5], m[6], m[7], t4);
+          if (r == pb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c > pb) continue;
+              double c0, c1;
+              if (c == pb) {
+                c0 = sel4(m[0], m[2], m[4], m[6], t4);
+                c1 = sel4(m[1], m[3], m[5], m[7], t4);
+              } else {
+                c0 = c1 = 0.0;
+                dmma884(c0, c1, l0, Mrow[c * TD + t4 * TS + gq]);
+                dmma884(c0, c1, l1, Mrow[c * TD + (4 + t4) * TS + gq]);
+              }
+              *reinterpret_cast<double2*>(Mp + c * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
+              LTs[(8 * c + 2 * t4) * LDT + 8 * pb + gq] = c0;
+              LTs[(8 * c + 2 * t4 + 1) * LDT + 8 * pb + gq] = c1;
+              // the finished row block goes out to global memory straight away (the tiles above
+              // the diagonal of LinvT are zero from allocation and are never written)
+              LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = c0;
+              LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = c1;
+            }
+          } else {
+            double c0 = 0.0, c1 = 0.0;
+            dmma884(c0, c1, Wcol[r * TD + gq * TS + t4], l0);
+            dmma884(c0, c1, Wcol[r * TD + gq * TS + 4 + t4], l1);
+            *reinterpret_cast<double2*>(Lp + r * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
           }
         }
-        if (p + 1 < NB) publish_row(p + 1);
+        __syncthreads();   // (B) Lp, Mp in place; Wcol / Mrow free again
+        if (r > pb) {
+          const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];
+#pragma unroll
+          for (int c = pb + 1; c < 8; ++c)
+            if (c <= r) {
+              dmma884(W.t[c][0], W.t[c][1], a0, Lp[c * TD + gq * TS + t4]);
+              dmma884(W.t[c][0], W.t[c][1], a1, Lp[c * TD + gq * TS + 4 + t4]);
+              if (c == pb + 1)   // next pivot column first, published straight away
+                *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[c][0], W.t[c][1]);
+            }
+#pragma unroll
+          for (int c = 0; c <= pb; ++c) {
+            dmma884(M.t[c][0], M.t[c][1], a0, Mp[c * TD + t4 * TS + gq]);
+            dmma884(M.t[c][0], M.t[c][1], a1, Mp[c * TD + (4 + t4) * TS + gq]);
+            if (r == pb + 1)
+              *reinterpret_cast<double2*>(Mrow + c * TD + gq * TS + 2 * t4) = make_double2(M.t[c][0], M.t[c][1]);
+          }
+        }
       }
       __syncthreads();
       BA_TRACE(t, 4);   // sweep done
       const bool bad = s_bad != 0;
-      if (bad && tid == 0) *g.status = 1.0;
-      if (tid < NB) isd[tid] = bad ? 1.0 : 1.0 / sqrt(piv[tid]);
+      if (bad) {   // leave an identity behind so that dependants stay finite
+        if (tid == 0) *g.status = 1.0;
+        for (int e = tid; e < NB * NB; e += kSolveThreads) {
+          const double v = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+          LTs[(e >> 6) * LDT + (e & 63)] = v;
+          LT[e] = v;
+        }
+      }
+      if (tid < NB) tvec[tid] = rhs_j - bacc;
+      __threadfence();
       __syncthreads();
-      // scaled inverse, transposed, into smem:  LTs[m*LDT + c'] = Linv[c'][m] = M[c'][m] isd[c']
-      // (on a failed pivot leave an identity behind so that dependants stay finite)
-      double* LTs = buf;
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            double v = (c <= r) ? M.v[mi][ni][e] * isd[r] : 0.0;
-            if (bad) v = (r == c) ? 1.0 : 0.0;
-            LTs[c * LDT + r] = v;
-          }
-      if (tid < NB) tvec[tid] = __ldcg(g.rhs + j * NB + tid) - bacc;
-      __syncthreads();
-      double* LT = g.LinvT + (size_t)j * NB * NB;
-      for (int e = tid; e < NB * NB; e += kSolveThreads) LT[e] = LTs[(e >> 6) * LDT + (e & 63)];
+      if (tid == 0) st_release(&g.flags[(size_t)j * T + j], epoch);   // L_jj^{-1} is out: panels may go
       // forward substitution: y_j = Linv (b_j - sum_k L_jk y_k);  thread r: sum_m LTs[m][r] t[m]
       if (tid < NB) {
         double s = 0.0;
 #pragma unroll 8
         for (int m = 0; m < NB; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
+        __threadfence();
       }
+      __syncthreads();
+      if (tid == 0) st_release(&yflag[j], epoch);
     } else {
-      // ---- panel tile: L_ij = (A_ij - acc) Linv_jj^T -----------------------------------------
+      // ================================ panel task =============================================
+      // C = A_ij - sum_k L_ik L_jk^T  (A_ij fetched up front),  then  L_ij = C Linv_jj^T
+      Frag acc;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
+            acc.v[mi][ni][e] = __ldcg(Aij + (size_t)c * ld + r);
+          }
+      auto issue = [&](int k) {
+        double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+        stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)i * NB, ld);
+        stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
+        cp_async_commit();
+      };
+      if (j > 0) {
+        wait_flag(&g.flags[(size_t)i * T + 0], epoch);
+        wait_flag(&g.flags[(size_t)j * T + 0], epoch);
+        __syncthreads();
+        issue(0);
+      }
+      for (int k = 0; k < j; ++k) {
+        if (k + 1 < j) {
+          wait_flag(&g.flags[(size_t)i * T + k + 1], epoch);
+          wait_flag(&g.flags[(size_t)j * T + k + 1], epoch);
+          __syncthreads();
+          issue(k + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+        tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
+        __syncthreads();
+      }
+      BA_TRACE(t, 3);   // k loop done
       double* Cs = buf;                  // [m][r] = C[r][m]
       double* Bs = buf + kTileDoubles;   // [m][c] = Linv[c][m]
 #pragma unroll
@@ -392,7 +517,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            Cs[c * LDT + r] = __ldcg(Aij + (size_t)c * ld + r) - acc.v[mi][ni][e];
+            Cs[c * LDT + r] = acc.v[mi][ni][e];
           }
       wait_flag(&g.flags[(size_t)j * T + j], epoch);
       __syncthreads();
@@ -403,7 +528,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       __syncthreads();
       Frag out;
       out.zero();
-      tile_dmma(out, Cs, Bs, R0, C0, lane);
+      tile_dmma<false>(out, Cs, Bs, R0, C0, lane);
       double* Lij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -414,11 +539,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
             Lij[(size_t)c * ld + r] = out.v[mi][ni][e];
           }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release(&g.flags[(size_t)i * T + j], epoch);
     }
-    // ---- publish ------------------------------------------------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release(&g.flags[(size_t)i * T + j], epoch);
     BA_TRACE(t, 5);   // published
   }
 
@@ -437,25 +561,41 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     BA_TRACE_SET(ntasks + bt, 0, (unsigned long long)k);
     BA_TRACE_SET(ntasks + bt, 1, (unsigned long long)blockIdx.x);
     BA_TRACE(ntasks + bt, 2);
-    wait_flag(&g.flags[(size_t)k * T + k], epoch);   // L_kk^{-1} and y_k
+    // everything this task reads except the x_i is long finished when it starts: wait for all of
+    // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
+    // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
+    if (tid == 0) {
+      while (ld_acquire(&g.flags[(size_t)k * T + k]) != epoch) __nanosleep(20);          // L_kk^{-1}
+      while (ld_acquire(&g.flags[(size_t)T * T + T + k]) != epoch) __nanosleep(20);      // y_k
+      for (int i = T - 1; i > k; --i)
+        while (ld_acquire(&g.flags[(size_t)i * T + k]) != epoch) __nanosleep(20);        // tiles (i, k)
+    }
     __syncthreads();
     {
       const double* LT = g.LinvT + (size_t)k * NB * NB;
       for (int e = tid; e < NB * NB; e += kSolveThreads) LTs[(e >> 6) * NBP + (e & 63)] = __ldcg(LT + e);
     }
+    const double yk_mine = (tid < NB) ? __ldcg(g.rhs + k * NB + tid) : 0.0;
     // warp w owns columns 8w .. 8w+7 of every tile; lanes span rows
-    double cs[8];
+    double cs[8], la[8], lb[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) cs[q] = 0.0;
+    auto fetch_tile = [&](int i) {
+      const double* Lik = g.A + (size_t)(k * NB + 8 * wid) * ld + (size_t)i * NB;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        la[q] = __ldcg(Lik + (size_t)q * ld + lane);
+        lb[q] = __ldcg(Lik + (size_t)q * ld + 32 + lane);
+      }
+    };
+    if (k < T - 1) fetch_tile(T - 1);
     for (int i = T - 1; i > k; --i) {
-      wait_flag(&g.flags[(size_t)i * T + k], epoch);       // tile (i, k) of L
       wait_flag(&g.flags[(size_t)T * T + i], epoch);       // x_i
       __syncthreads();
       const double x0 = __ldcg(g.x + i * NB + lane), x1 = __ldcg(g.x + i * NB + 32 + lane);
-      const double* Lik = g.A + (size_t)(k * NB + 8 * wid) * ld + (size_t)i * NB;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        cs[q] += __ldcg(Lik + (size_t)q * ld + lane) * x0 + __ldcg(Lik + (size_t)q * ld + 32 + lane) * x1;
+      for (int q = 0; q < 8; ++q) cs[q] += la[q] * x0 + lb[q] * x1;
+      if (i - 1 > k) fetch_tile(i - 1);
     }
     BA_TRACE(ntasks + bt, 3);   // all x_i folded
 #pragma unroll
@@ -464,7 +604,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       if (lane == 0) accv[8 * wid + q] = s;
     }
     __syncthreads();
-    if (tid < NB) accv[tid] = __ldcg(g.rhs + k * NB + tid) - accv[tid];
+    if (tid < NB) accv[tid] = yk_mine - accv[tid];
     __syncthreads();
     // x_k[c] = sum_m Linv[m][c] acc[m] = sum_m LinvT[c][m] acc[m];  4 partial sums per c
     {
