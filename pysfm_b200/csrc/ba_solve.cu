@@ -105,7 +105,28 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
   do {                                                                             \
     if (g.trace && threadIdx.x == 0) g.trace[(size_t)(rec) * 8 + (slot)] = (v);    \
   } while (0)
+__device__ long long g_sweep_clk[64];
+#define BA_CLK(idx)                                                                \
+  do {                                                                             \
+    if (t == 0 && tid == 224) g_sweep_clk[(idx)] = clock64();                      \
+  } while (0)
+#define BA_CLK0(idx)                                                               \
+  do {                                                                             \
+    if (t == 0 && tid == 0) g_sweep_clk[(idx)] = clock64();                        \
+  } while (0)
+// clock read that waits for the value `dep` (a load result or accumulator) to exist
+#define BA_CLK_DEP(idx, dep)                                                       \
+  do {                                                                             \
+    if (t == 0 && tid == 224) {                                                    \
+      long long c__;                                                               \
+      asm volatile("{ .reg .f64 z; add.f64 z, %1, 0d0000000000000000; mov.u64 %0, %%clock64; }" : "=l"(c__) : "d"(dep)); \
+      g_sweep_clk[(idx)] = c__;                                                    \
+    }                                                                              \
+  } while (0)
 #else
+#define BA_CLK(idx) do { } while (0)
+#define BA_CLK0(idx) do { } while (0)
+#define BA_CLK_DEP(idx, dep) do { } while (0)
 #define BA_TRACE_DECL
 #define BA_TRACE(rec, slot) do { } while (0)
 #define BA_TRACE_SET(rec, slot, v) do { } while (0)
@@ -337,112 +358,184 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
       BA_TRACE(t, 3);   // k loop done
 
-      // ---- blocked sweep: 8 panel steps of 8 pivots.  Step pb: every warp r >= pb factors the
-      // 8x8 pivot block D redundantly (Gauss-Jordan in registers, one row per lane quad) into
-      // Linv_d = L_d^{-1};  warp r > pb forms its panel tile Lp_r = W(r,pb) Linv_d^T, warp pb
-      // the finished row block of the inverse  Mp_c = Linv_d M(pb,c);  after one barrier the
-      // trailing tiles take the rank-8 update  W(r,c) -= Lp_r Lp_c^T,  M(r,c) -= Lp_r Mp_c
-      // on the FP64 tensor pipe.  M accumulates L~^{-1} exactly as in a Gauss-Jordan sweep of
-      // [W | I], so the row blocks Mp are the rows of L_jj^{-1}; L_jj itself is never needed.
+      // ---- blocked sweep: 8 panel steps of 8 pivots ------------------------------------------
+      // Step pb:  warp 0 (whose row block holds no trailing tiles) factors the 8x8 pivot block
+      // D = W(pb,pb) by Gauss-Jordan in registers into Linv_d = L_d^{-1} and shares it through
+      // shared memory;  warp r > pb forms its panel tile  Lp_r = W(r,pb) Linv_d^T,  warp pb the
+      // finished row block of the inverse  Mp_c = Linv_d M(pb,c);  then the trailing tiles take
+      // the rank-8 update  W(r,c) -= Lp_r Lp_c^T,  M(r,c) -= Lp_r Mp_c  on the FP64 tensor pipe.
+      // M accumulates L~^{-1} exactly as a Gauss-Jordan sweep of [W | I] would, so the row
+      // blocks Mp are the rows of L_jj^{-1}; L_jj itself is never needed.
+      // Lookahead: the owner of row block pb+1 updates the next pivot block FIRST and hands it
+      // to warp 0 through a 64-thread named barrier, so the latency-bound Gauss-Jordan of step
+      // pb+1 runs concurrently with the rest of the trailing update of step pb.
       double* const LTs = buf;                          // [m][c'] = Linv[c'][m], row stride LDT
       double* const Wcol = buf + kTileDoubles;          // [8][TD]  column block pb of W
       double* const Mrow = Wcol + 8 * TD;               // [8][TD]  row block pb of M
       double* const Lp = Mrow + 8 * TD;                 // [8][TD]  panel tiles
       double* const Mp = Lp + 8 * TD;                   // [8][TD]  row block pb of Linv
+      double* const Dn = Mp + 8 * TD;                   // [TD]     next pivot block, [row][col]
+      double* const Ld = Dn + TD;                       // [TD]     Linv_d, [row][col]
+      BA_CLK(33);
       RowTiles M;
 #pragma unroll
       for (int c = 0; c < 8; ++c) M.t[c][0] = M.t[c][1] = 0.0;
-      for (int e = tid; e < NB * LDT; e += kSolveThreads) LTs[e] = 0.0;
       if (tid == 0) s_bad = 0;
-      *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[0][0], W.t[0][1]);
+      if (r == 0) {
+        *reinterpret_cast<double2*>(Dn + gq * TS + 2 * t4) = make_double2(W.t[0][0], W.t[0][1]);
+        __syncwarp();
+      } else {
+        *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[0][0], W.t[0][1]);
+      }
 #pragma unroll
       for (int pb = 0; pb < 8; ++pb) {
-        __syncthreads();   // (A) Wcol tiles r >= pb and Mrow tiles c < pb are in place
-        if (r >= pb) {
-          double w[8], m[8];
-          {
-            const double* drow = Wcol + pb * TD + gq * TS;
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              const double2 v = *reinterpret_cast<const double2*>(drow + c);
-              w[c] = v.x; w[c + 1] = v.y;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) m[c] = (c == gq) ? 1.0 : 0.0;
-          double dmine = 1.0;
+        double l0 = 0.0, l1 = 0.0;   // Linv_d[gq][t4], Linv_d[gq][t4 + 4]: the DMMA operand layout
+        if (r == 0) {
+          if (pb > 0) asm volatile("bar.sync 1, 64;" ::: "memory");   // D_pb is in Dn
+          BA_CLK0(pb * 4 + 0);
+          // Lane (gq, t4) holds columns t4 and t4 + 4 of row gq of D and of the accumulated
+          // inverse M.  Elimination by 2x2 pivot blocks: one reciprocal (of the block
+          // determinant) sits on the dependency chain per TWO pivots.  After the four block
+          // steps M D M^T is block diagonal with the 2x2 Schur complements [[a, b], [b, c]];
+          // their Cholesky inverses  [[1/sqrt(a), 0], [-b/(a s), 1/s]],  s = sqrt(det / a),
+          // are folded into the rows afterwards, off the chain.
+          double w0 = Dn[gq * TS + t4], w1 = Dn[gq * TS + 4 + t4];
+          double m0 = (gq == t4) ? 1.0 : 0.0, m1 = (gq == t4 + 4) ? 1.0 : 0.0;
           bool bad = false;
+          double pa = 1.0, pb_ = 0.0, pdet = 1.0;   // this lane's row: its block's a, b, det
+          const int quad = lane & 28;
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            double d = __shfl_sync(0xffffffffu, w[p], 4 * p);
-            if (!(d >= 1e-290)) { bad = true; d = 1.0; }  // also catches NaN; warp-uniform
-            if (gq == p) dmine = d;
-            double u[8], um[8];
-#pragma unroll
-            for (int c = p + 1; c < 8; ++c) u[c] = __shfl_sync(0xffffffffu, w[c], 4 * p);
-#pragma unroll
-            for (int c = 0; c < p; ++c) um[c] = __shfl_sync(0xffffffffu, m[c], 4 * p);
-            const double f = ((gq > p) ? w[p] : 0.0) * pivot_rcp(d);
-#pragma unroll
-            for (int c = p + 1; c < 8; ++c) w[c] -= f * u[c];
-#pragma unroll
-            for (int c = 0; c < p; ++c) m[c] -= f * um[c];
-            m[p] -= f;
+          for (int p = 0; p < 8; p += 2) {
+            const double wh = (p < 4) ? w0 : w1;        // the half that holds columns p, p + 1
+            double a = __shfl_sync(0xffffffffu, wh, 4 * p + (p & 3));
+            const double b = __shfl_sync(0xffffffffu, wh, 4 * p + ((p + 1) & 3));
+            const double c = __shfl_sync(0xffffffffu, wh, 4 * (p + 1) + ((p + 1) & 3));
+            const double wgp = __shfl_sync(0xffffffffu, wh, quad | (p & 3));          // D[gq][p]
+            const double wgp1 = __shfl_sync(0xffffffffu, wh, quad | ((p + 1) & 3));   // D[gq][p+1]
+            double det = a * c - b * b;
+            if (!(a >= 1e-290) || !(det >= 1e-290 * a)) { bad = true; a = 1.0; det = 1.0; }  // warp-uniform; catches NaN
+            if ((gq >> 1) == (p >> 1)) { pa = a; pb_ = b; pdet = det; }
+            const double idet = pivot_rcp(det);
+            const bool below = gq > p + 1;
+            const double f0 = below ? (wgp * c - wgp1 * b) * idet : 0.0;
+            const double f1 = below ? (wgp1 * a - wgp * b) * idet : 0.0;
+            // rows p and p + 1, this lane's columns (columns <= p + 1 of W are dead, M is zero
+            // beyond column p + 1: those halves are skipped statically)
+            if (p < 2) {
+              const double u0 = __shfl_sync(0xffffffffu, w0, 4 * p + t4), u1 = __shfl_sync(0xffffffffu, w0, 4 * (p + 1) + t4);
+              w0 -= f0 * u0 + f1 * u1;
+            }
+            if (p < 6) {
+              const double u0 = __shfl_sync(0xffffffffu, w1, 4 * p + t4), u1 = __shfl_sync(0xffffffffu, w1, 4 * (p + 1) + t4);
+              w1 -= f0 * u0 + f1 * u1;
+            }
+            {
+              const double u0 = __shfl_sync(0xffffffffu, m0, 4 * p + t4), u1 = __shfl_sync(0xffffffffu, m0, 4 * (p + 1) + t4);
+              m0 -= f0 * u0 + f1 * u1;
+            }
+            if (p >= 4) {
+              const double u0 = __shfl_sync(0xffffffffu, m1, 4 * p + t4), u1 = __shfl_sync(0xffffffffu, m1, 4 * (p + 1) + t4);
+              m1 -= f0 * u0 + f1 * u1;
+            }
           }
           if (bad && lane == 0) s_bad = 1;
-          const double isd = rsqrt(dmine);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) m[c] *= isd;        // row gq of Linv_d
-          const double l0 = sel4(m[0], m[1], m[2], m[3], t4), l1 = sel4(m[4], m[5], m[6], m[7], t4);
-          if (r == pb) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (c > pb) continue;
-              double c0, c1;
-              if (c == pb) {
-                c0 = sel4(m[0], m[2], m[4], m[6], t4);
-                c1 = sel4(m[1], m[3], m[5], m[7], t4);
-              } else {
-                c0 = c1 = 0.0;
-                dmma884(c0, c1, l0, Mrow[c * TD + t4 * TS + gq]);
-                dmma884(c0, c1, l1, Mrow[c * TD + (4 + t4) * TS + gq]);
-              }
-              *reinterpret_cast<double2*>(Mp + c * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
-              LTs[(8 * c + 2 * t4) * LDT + 8 * pb + gq] = c0;
-              LTs[(8 * c + 2 * t4 + 1) * LDT + 8 * pb + gq] = c1;
-              // the finished row block goes out to global memory straight away (the tiles above
-              // the diagonal of LinvT are zero from allocation and are never written)
-              LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = c0;
-              LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = c1;
-            }
-          } else {
-            double c0 = 0.0, c1 = 0.0;
-            dmma884(c0, c1, Wcol[r * TD + gq * TS + t4], l0);
-            dmma884(c0, c1, Wcol[r * TD + gq * TS + 4 + t4], l1);
-            *reinterpret_cast<double2*>(Lp + r * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
+          BA_CLK0(pb * 4 + 1);
+          {
+            const double isa = rsqrt(pa), isd = rsqrt(pdet);   // independent of each other
+            const double is = isd * (pa * isa);                // 1 / sqrt(det / a)
+            const double tb = is * pb_ * (isa * isa);
+            const bool odd = gq & 1;
+            const double up0 = __shfl_up_sync(0xffffffffu, m0, 4), up1 = __shfl_up_sync(0xffffffffu, m1, 4);   // row gq - 1
+            l0 = odd ? is * m0 - tb * up0 : isa * m0;
+            l1 = odd ? is * m1 - tb * up1 : isa * m1;
           }
+          Ld[gq * TS + t4] = l0;
+          Ld[gq * TS + 4 + t4] = l1;
+          BA_CLK0(pb * 4 + 2);
         }
-        __syncthreads();   // (B) Lp, Mp in place; Wcol / Mrow free again
+        __syncthreads();   // (X) Linv_d, Wcol tiles r > pb and Mrow tiles c < pb are in place
+        if (r >= pb && r > 0) {
+          l0 = Ld[gq * TS + t4];
+          l1 = Ld[gq * TS + 4 + t4];
+        }
+        if (r == pb) {
+          // finished row block pb of the inverse:  Mp_c = Linv_d M(pb, c), c < pb;  Mp_pb = Linv_d.
+          // It goes to Mp (operand of the update), to LTs (forward substitution) and straight
+          // out to global memory (the tiles above the diagonal of LinvT are zero from allocation
+          // and are never written).
+          Mp[pb * TD + gq * TS + t4] = l0;
+          Mp[pb * TD + gq * TS + 4 + t4] = l1;
+          LTs[(8 * pb + t4) * LDT + 8 * pb + gq] = l0;
+          LTs[(8 * pb + 4 + t4) * LDT + 8 * pb + gq] = l1;
+          LT[(8 * pb + t4) * NB + 8 * pb + gq] = l0;
+          LT[(8 * pb + 4 + t4) * NB + 8 * pb + gq] = l1;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c >= pb) break;
+            double c0 = 0.0, c1 = 0.0;
+            dmma884(c0, c1, l0, Mrow[c * TD + t4 * TS + gq]);
+            dmma884(c0, c1, l1, Mrow[c * TD + (4 + t4) * TS + gq]);
+            *reinterpret_cast<double2*>(Mp + c * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
+            LTs[(8 * c + 2 * t4) * LDT + 8 * pb + gq] = c0;
+            LTs[(8 * c + 2 * t4 + 1) * LDT + 8 * pb + gq] = c1;
+            LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = c0;
+            LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = c1;
+          }
+        } else if (r > pb) {
+          double c0 = 0.0, c1 = 0.0;
+          dmma884(c0, c1, Wcol[r * TD + gq * TS + t4], l0);
+          dmma884(c0, c1, Wcol[r * TD + gq * TS + 4 + t4], l1);
+          *reinterpret_cast<double2*>(Lp + r * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
+        }
+        __syncthreads();   // (Y) Lp, Mp in place; Wcol / Mrow / Ld free again
+        BA_CLK(pb * 4 + 3);
         if (r > pb) {
           const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];
-#pragma unroll
-          for (int c = pb + 1; c < 8; ++c)
-            if (c <= r) {
-              dmma884(W.t[c][0], W.t[c][1], a0, Lp[c * TD + gq * TS + t4]);
-              dmma884(W.t[c][0], W.t[c][1], a1, Lp[c * TD + gq * TS + 4 + t4]);
-              if (c == pb + 1)   // next pivot column first, published straight away
-                *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[c][0], W.t[c][1]);
+          if (pb + 1 < 8) {
+            // next pivot column first: publish it, and hand the next pivot block to warp 0
+            const int c = pb + 1 < 8 ? pb + 1 : 7;   // == pb + 1 (kept in range for the unroller)
+            dmma884(W.t[c][0], W.t[c][1], a0, Lp[c * TD + gq * TS + t4]);
+            dmma884(W.t[c][0], W.t[c][1], a1, Lp[c * TD + gq * TS + 4 + t4]);
+            if (r == pb + 1) {
+              *reinterpret_cast<double2*>(Dn + gq * TS + 2 * t4) = make_double2(W.t[c][0], W.t[c][1]);
+              __threadfence_block();
+              asm volatile("bar.arrive 1, 64;" ::: "memory");
+            } else {
+              *reinterpret_cast<double2*>(Wcol + r * TD + gq * TS + 2 * t4) = make_double2(W.t[c][0], W.t[c][1]);
             }
+          }
+          // the rest: all operands first, then two rounds of independent DMMAs
+          double b0[8], b1[8];
 #pragma unroll
-          for (int c = 0; c <= pb; ++c) {
-            dmma884(M.t[c][0], M.t[c][1], a0, Mp[c * TD + t4 * TS + gq]);
-            dmma884(M.t[c][0], M.t[c][1], a1, Mp[c * TD + (4 + t4) * TS + gq]);
-            if (r == pb + 1)
-              *reinterpret_cast<double2*>(Mrow + c * TD + gq * TS + 2 * t4) = make_double2(M.t[c][0], M.t[c][1]);
+          for (int c = 0; c < 8; ++c) {
+            b0[c] = b1[c] = 0.0;
+            if (c == pb + 1 || c > r) continue;
+            const double* q = (c > pb) ? Lp + c * TD + gq * TS + t4 : Mp + c * TD + t4 * TS + gq;
+            b0[c] = q[0];
+            b1[c] = q[(c > pb) ? 4 : 4 * TS];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c == pb + 1) continue;
+            if (c > pb) { if (c <= r) dmma884(W.t[c][0], W.t[c][1], a0, b0[c]); }
+            else dmma884(M.t[c][0], M.t[c][1], a0, b0[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c == pb + 1) continue;
+            if (c > pb) { if (c <= r) dmma884(W.t[c][0], W.t[c][1], a1, b1[c]); }
+            else dmma884(M.t[c][0], M.t[c][1], a1, b1[c]);
+          }
+          if (r == pb + 1) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c <= pb) *reinterpret_cast<double2*>(Mrow + c * TD + gq * TS + 2 * t4) = make_double2(M.t[c][0], M.t[c][1]);
           }
         }
+        BA_CLK(36 + pb * 3);
       }
       __syncthreads();
+      BA_CLK(32);
       BA_TRACE(t, 4);   // sweep done
       const bool bad = s_bad != 0;
       if (bad) {   // leave an identity behind so that dependants stay finite
@@ -458,10 +551,12 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       __syncthreads();
       if (tid == 0) st_release(&g.flags[(size_t)j * T + j], epoch);   // L_jj^{-1} is out: panels may go
       // forward substitution: y_j = Linv (b_j - sum_k L_jk y_k);  thread r: sum_m LTs[m][r] t[m]
+      // (the 8x8 tiles of LTs above the block diagonal were never written: stop at the diagonal tile)
       if (tid < NB) {
         double s = 0.0;
+        const int mend = 8 * ((tid >> 3) + 1);
 #pragma unroll 8
-        for (int m = 0; m < NB; ++m) s += LTs[m * LDT + tid] * tvec[m];
+        for (int m = 0; m < mend; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
         __threadfence();
       }

@@ -87,5 +87,12 @@ int main(int argc, char** argv) {
     printf("%4d (%3d,%3d) %4llu %9.2f %9.2f %9.2f %9.2f\n", t, i, j, r[1], (r[2] - t0) * 1e-3, (r[3] - t0) * 1e-3,
            r[4] ? (r[4] - t0) * 1e-3 : 0.0, (r[5] - t0) * 1e-3);
   }
+  long long clk[64];
+  CK(cudaMemcpyFromSymbol(clk, ba::g_sweep_clk, sizeof clk));
+  printf("sweep of task 0 (warp 7), clocks since k-loop end: ");
+  for (int pb = 0; pb < 8; ++pb)
+    printf("\n  pb=%d  gj_start %lld  gj_done %lld  Ld_out %lld  postY(w7) %lld  update_done(w7) %lld", pb, clk[pb * 4] - clk[33], clk[pb * 4 + 1] - clk[33],
+           clk[pb * 4 + 2] - clk[33], clk[pb * 4 + 3] - clk[33], clk[36 + pb * 3] - clk[33]);
+  printf("\n  end %lld\n", clk[32] - clk[33]);
   return 0;
 }
