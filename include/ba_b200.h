@@ -137,6 +137,19 @@ int ba_accept(ba_handle h);
  * (BA_OK or BA_ERR_ILLCONDITIONED).  The only synchronising call on the product path. */
 int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_status,
                     void* stream);
+/* One whole LM trial driven from HOST buffers -- what BundleAdjuster.compute_update
+ * (bundle_adjuster.py:176-208) plus the candidate cost of optimize (:143-146) amount to when the
+ * bundle lives in host memory: H2D of the current estimate (cam_R [n_cam][9], cam_t [n_cam][3],
+ * pts [n_pt][3]; any may be NULL = keep the device copy), ba_linearize_eliminate(BA_WANT_SCHUR),
+ * ba_solve, ba_backsub_retract_cost, D2H of dC [6 n_opt_cam] and dP [n_pt][3] (either may be
+ * NULL) and of the scalars, ONE stream synchronisation at the end.  Single-GPU handles only
+ * (sharded problems need the host-side all-reduce between the stages).  Pass pinned host memory
+ * for the copies to be asynchronous. */
+int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_host,
+                  const double* pts_host, double damping, double pinv_rcond,
+                  const unsigned char* cam_param_mask_host, double* dC_host, double* dP_host,
+                  double* cost, double* cand_cost, int* solve_status, void* stream);
+
 /* Device address of the 4-double scalar record {cost, cand_cost, status, spare} so the host
  * side can all-reduce the two costs when points are sharded over ranks. */
 int ba_scalars_ptr(ba_handle h, double** scalars_dev);

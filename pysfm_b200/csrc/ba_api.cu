@@ -246,6 +246,31 @@ int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_sta
   return BA_OK;
 }
 
+int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_host,
+                  const double* pts_host, double damping, double pinv_rcond,
+                  const unsigned char* cam_param_mask_host, double* dC_host, double* dP_host,
+                  double* cost, double* cand_cost, int* solve_status, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h) || !h->sys || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  if (cam_R_host)
+    BA_CUDA(h, cudaMemcpyAsync(h->state.cam_R, cam_R_host, (size_t)h->n_cam * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (cam_t_host)
+    BA_CUDA(h, cudaMemcpyAsync(h->state.cam_t, cam_t_host, (size_t)h->n_cam * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (pts_host)
+    BA_CUDA(h, cudaMemcpyAsync(h->state.pts, pts_host, (size_t)h->n_pt * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = ba_linearize_eliminate(h, damping, pinv_rcond, BA_WANT_SCHUR, stream);
+  if (rc != BA_OK) return rc;
+  if ((rc = ba_solve(h, cam_param_mask_host, stream)) != BA_OK) return rc;
+  if ((rc = ba_backsub_retract_cost(h, stream)) != BA_OK) return rc;
+  if (dC_host && h->n_sys)
+    BA_CUDA(h, cudaMemcpyAsync(dC_host, h->dC, (size_t)h->n_sys * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (dP_host)
+    BA_CUDA(h, cudaMemcpyAsync(dP_host, h->dP, (size_t)h->n_pt * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return ba_read_scalars(h, cost, cand_cost, solve_status, stream);
+}
+
 int ba_scalars_ptr(ba_handle h, double** p) {
   if (!h || !p) return BA_ERR_BAD_ARGUMENT;
   *p = reinterpret_cast<double*>(h->scalars);

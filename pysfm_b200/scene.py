@@ -313,6 +313,33 @@ class DeviceProblem(object):
         self._chk(self.lib.ba_get_array(self.h, _lib.BA_ARR_DP, ctypes.c_void_p(out_dP.data_ptr()),
                                         3 * self.scene.n_pt, self._stream()), "ba_get_array")
 
+    def trial_host(self, damping, rcond, cam_R=None, cam_t=None, pts=None, out_dC=None, out_dP=None,
+                   cam_param_mask=None):
+        """One whole LM trial from HOST buffers through ba_trial_host: H2D of the estimate (torch
+        CPU tensors, pinned for asynchronous copies; None keeps the device copy), the three
+        stages, D2H of dC / dP into caller tensors, one synchronisation.
+        Returns (cost, candidate cost, status)."""
+        sc = self.scene
+        ptr = lambda t, n: None if t is None else (self._host_ptr(t, n))
+        mp = None
+        if cam_param_mask is not None:
+            m = np.ascontiguousarray(cam_param_mask, dtype=np.uint8)
+            assert m.shape == (self.n_sys,), 'shape was ' + str(m.shape)
+            self._mask_keepalive = m
+            mp = m.ctypes.data_as(ctypes.c_void_p)
+        cost, cand = ctypes.c_double(), ctypes.c_double()
+        status = ctypes.c_int()
+        self._chk(self.lib.ba_trial_host(self.h, ptr(cam_R, 9 * sc.n_cam), ptr(cam_t, 3 * sc.n_cam), ptr(pts, 3 * sc.n_pt),
+                                         float(damping), float(rcond), mp, ptr(out_dC, self.n_sys),
+                                         ptr(out_dP, 3 * sc.n_pt), ctypes.byref(cost), ctypes.byref(cand),
+                                         ctypes.byref(status), self._stream()), "ba_trial_host")
+        return cost.value, cand.value, status.value
+
+    def _host_ptr(self, t, count):
+        assert (not t.is_cuda) and t.dtype == self.torch.float64 and t.is_contiguous() and t.numel() == count, \
+            'expected a contiguous float64 CPU tensor of %d elements' % count
+        return ctypes.c_void_p(t.data_ptr())
+
     def read_scalars(self):
         cost, cand = ctypes.c_double(), ctypes.c_double()
         status = ctypes.c_int()

@@ -197,3 +197,57 @@ def test_illconditioned_raises(cuda_device):
         S[i, i] = -np.eye(6)
     with pytest.raises(NormalEquationsIllconditioned):
         ba.solve_motion_normal_eqns(S, np.ones((nc, 6)), np.ones(6 * nc, bool))
+
+
+def test_trial_host_single_call_matches_staged_path(cuda_device):
+    """ba_trial_host (estimate from pinned host memory, one C-ABI call, one synchronisation) gives
+    the same update and costs as the staged calls, and as the oracle."""
+    import torch
+    from oracle import ba_oracle
+    from pysfm_b200 import synthetic
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+    n_cam, n_pt, k, seed, damping = 25, 1500, 6, 21, 3.0
+    a = synthetic.make_arrays(n_cam, n_pt, k, seed)
+    b = synthetic.make_scene(n_cam, n_pt, k, seed)
+    ba = BundleAdjuster(b, device=cuda_device, verbose=False)
+    motion, structure = ba.compute_update(damping)
+    p = ba._problem
+    sc = p.scene
+    pin = lambda arr: torch.as_tensor(np.ascontiguousarray(arr), dtype=torch.float64).reshape(-1).pin_memory()
+    out_dC = torch.empty(p.n_sys, dtype=torch.float64).pin_memory()
+    out_dP = torch.empty(3 * sc.n_pt, dtype=torch.float64).pin_memory()
+    # scramble the device state first: the call must really upload the host estimate
+    p.upload_state(np.tile(np.eye(3).reshape(1, 9), (sc.n_cam, 1)), np.zeros((sc.n_cam, 3)), np.ones((sc.n_pt, 3)))
+    cost, cand, st = p.trial_host(damping, 1e-5, pin(sc.cam_R), pin(sc.cam_t), pin(sc.pts), out_dC, out_dP)
+    assert st == 0
+    assert relerr(-out_dC.numpy().reshape(-1, 6), motion) < 1e-12
+    assert relerr(-out_dP.numpy().reshape(-1, 3)[ba._packed.optim_track_indices], structure) < 1e-12
+    P = ba_oracle.Problem(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"],
+                          ('gaussian', np.eye(2)), np.arange(1, n_cam), np.arange(n_pt))
+    assert abs(cost - ba_oracle.compute_cost(P)) < 1e-10 * cost
+    m2, s2 = ba_oracle.compute_update(P, damping)
+    assert relerr(-out_dC.numpy().reshape(-1, 6), m2) < 1e-7
+
+
+@pytest.mark.parametrize("nc", [1, 10, 11, 64, 200, 500])
+def test_reduced_solve_random_spd_systems(nc, cuda_device):
+    """solve_motion_normal_eqns on dense SPD systems whose size exercises 1 .. 47 solver tiles,
+    a partial last tile and a frozen-parameter mask, against numpy.linalg.solve."""
+    from pysfm_b200 import synthetic
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+    b = synthetic.make_scene(nc + 1, 40, min(nc + 1, 4), 31)
+    ba = BundleAdjuster(b, device=cuda_device, verbose=False)
+    rs = np.random.RandomState(100 + nc)
+    n = 6 * nc
+    G = rs.randn(n, n + 5)
+    A = G @ G.T / n + np.diag(rs.rand(n) + 0.5)
+    rhs = rs.randn(n)
+    S = A.reshape(nc, 6, nc, 6).transpose(0, 2, 1, 3).copy()
+    x = ba.solve_motion_normal_eqns(S, rhs.reshape(nc, 6), np.ones(n, bool))
+    assert relerr(x.flatten(), np.linalg.solve(A, rhs)) < 1e-9
+    mask = rs.rand(n) > 0.3
+    mask[0] = True
+    x = ba.solve_motion_normal_eqns(S, rhs.reshape(nc, 6), mask)
+    ref = np.zeros(n)
+    ref[mask] = np.linalg.solve(A[mask][:, mask], rhs[mask])
+    assert relerr(x.flatten(), ref) < 1e-9
