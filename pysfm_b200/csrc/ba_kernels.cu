@@ -70,6 +70,7 @@ struct ElimArgs {
   ObsArgs o;
   double damping, rcond;
   int n_opt_cam, kcap;
+  int probe;                   // timing probes (tools/elim_probe.py): 1 = skip the reductions, 2 = skip phase D
   size_t rhs_off;              // doubles of packed blocks before the right-hand side
   double* __restrict__ sys;    // packed upper 6x6 blocks (row by row), then rhs [6 n_opt_cam]
   double* __restrict__ Vinv;   // [n_pt][9]
@@ -134,18 +135,53 @@ linearize_eliminate_kernel(const ElimArgs A) {
   double* __restrict__ rhs = A.sys + A.rhs_off;
 
   double cost_acc = 0.0;
-  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
-    const int beg = o.pt_ptr[pt];
-    const int k = o.pt_ptr[pt + 1] - beg;
-    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
-    const bool pt_free = o.pt_slot[pt] >= 0;
+  // Two-deep software pipeline over the warp's points: the CSR range of the point after next and
+  // the first 32 observation records (+ coordinates) of the next point are fetched while the
+  // current point is processed, so that the dependent HBM round trips (pt_ptr -> record ->
+  // camera) are off the per-point critical path.  Cameras stay L1/L2 resident.
+  const int stride = gridDim.x * warps_per_cta;
+  int pt = blockIdx.x * warps_per_cta + wid;
+  int cur_beg = 0, cur_end = 0, nxt_beg = 0, nxt_end = 0;
+  if (pt < o.n_pt) { cur_beg = o.pt_ptr[pt]; cur_end = o.pt_ptr[pt + 1]; }
+  if (pt + stride < o.n_pt) { nxt_beg = o.pt_ptr[pt + stride]; nxt_end = o.pt_ptr[pt + stride + 1]; }
+  int pf_cam = 0, pf_ptslot = -1;
+  double2 pf_uv = make_double2(0.0, 0.0);
+  double pf_x0 = 0.0, pf_x1 = 0.0, pf_x2 = 0.0;
+  if (pt < o.n_pt) {
+    pf_x0 = o.pts[3 * pt]; pf_x1 = o.pts[3 * pt + 1]; pf_x2 = o.pts[3 * pt + 2];
+    pf_ptslot = o.pt_slot[pt];
+    if (lane < cur_end - cur_beg) {
+      pf_cam = o.obs_cam[cur_beg + lane];
+      pf_uv = reinterpret_cast<const double2*>(o.obs_uv)[cur_beg + lane];
+    }
+  }
+  for (; pt < o.n_pt; pt += stride) {
+    const int beg = cur_beg;
+    const int k = cur_end - cur_beg;
+    const double x[3] = {pf_x0, pf_x1, pf_x2};
+    const bool pt_free = pf_ptslot >= 0;
+    const int cam0 = pf_cam;
+    const double2 uv0 = pf_uv;
+    {   // advance the pipeline
+      const int p1 = pt + stride, p2 = pt + 2 * stride;
+      cur_beg = nxt_beg; cur_end = nxt_end;
+      if (p2 < o.n_pt) { nxt_beg = o.pt_ptr[p2]; nxt_end = o.pt_ptr[p2 + 1]; }
+      if (p1 < o.n_pt) {
+        pf_x0 = o.pts[3 * p1]; pf_x1 = o.pts[3 * p1 + 1]; pf_x2 = o.pts[3 * p1 + 2];
+        pf_ptslot = o.pt_slot[p1];
+        if (lane < cur_end - cur_beg) {
+          pf_cam = o.obs_cam[cur_beg + lane];
+          pf_uv = reinterpret_cast<const double2*>(o.obs_uv)[cur_beg + lane];
+        }
+      }
+    }
     double Vl[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
 
     // ---- phase A: lanes over observations ------------------------------------------------
     for (int a = lane; a < k; a += 32) {
       const int ob = beg + a;
-      const int cam = o.obs_cam[ob];
-      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      const int cam = (a < 32) ? cam0 : o.obs_cam[ob];
+      const double2 uv = (a < 32) ? uv0 : reinterpret_cast<const double2*>(o.obs_uv)[ob];
       const int slot = o.cam_slot[cam];
       double r[2], Jc[12], Jp[6];
       observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
@@ -233,7 +269,7 @@ linearize_eliminate_kernel(const ElimArgs A) {
     // point, so (a, b) is always in the stored upper block triangle. --------------------------
     // Pair order: the k diagonal pairs (a, a) first, then the k(k-1)/2 pairs a < b row by row,
     // so that only the first round(s) carry the Jc^T Jc term.
-    const int npairs = k * (k + 1) / 2;
+    const int npairs = (A.probe == 2) ? 0 : k * (k + 1) / 2;
     for (int q0 = 0; q0 < npairs; q0 += 32) {
       const int q = q0 + lane;
       // the previous round's (or point's) reduction must have finished READING this slot
@@ -277,7 +313,7 @@ linearize_eliminate_kernel(const ElimArgs A) {
               *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
+          if (A.probe != 1) bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
         }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -514,6 +550,7 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
                                        cudaStream_t st) {
   const bool blocks = flags & 1, schur = flags & 2;
   cudaError_t e;
+  const int probe = (flags >> 4) & 3;
   if (schur) {
     e = cudaMemsetAsync(c.sys, 0, c.sys_len * sizeof(double), st);
     if (e != cudaSuccess) return e;
@@ -525,6 +562,7 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   ElimArgs A;
   A.o = make_obs_args(c, c.state);
   A.damping = damping; A.rcond = rcond; A.n_opt_cam = c.n_opt_cam;
+  A.probe = probe;
   A.rhs_off = c.sys_len - (size_t)c.n_sys;
   int kcap = c.max_track_len < 1 ? 1 : c.max_track_len;
   A.kcap = kcap;
