@@ -312,14 +312,35 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         n = prob.n_sys
         n_pt_local, n_obs_local = sc.n_pt, sc.n_obs
-        # algorithmic bytes of ONE linearize_eliminate launch:
-        #   20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + S triangle + rhs written once + cameras
+        # Algorithmic bytes per launch of the three kernels of an iteration, their
+        # CUDA-event times of this run, and the DRAM traffic ncu measured for one launch of each
+        # (profiles/r1f_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum, --set full capture
+        # of this same command at N=1; the reduced system and the factor stay L2-resident, which is
+        # why the traffic is BELOW the algorithmic bytes for the first two).
+        #   linearize_eliminate: 20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + packed S + rhs + cameras
+        #   chol_dataflow:       packed system read once + dense factor written once and read once by the substitutions
+        #   backsub_cost:        20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24, dP 24, x' 24)
         elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * sc.n_cam
-        elim_s = stage_ms["linearize_eliminate"] * 1e-3
-        achieved = elim_bytes / elim_s / 1e9
+        solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (prob.ld * (prob.ld + 1) // 2)
+        back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * sc.n_cam
+        ncu_traffic = {"linearize_eliminate_kernel": 17417984, "chol_dataflow_kernel": 6373632,
+                       "backsub_cost_kernel": 16487168} if world == 1 else {}
+        kern = [("linearize_eliminate_kernel", elim_bytes, stage_ms["linearize_eliminate"],
+                 "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.75e11 adds/s = 0.172 ms"),
+                ("chol_dataflow_kernel", solve_bytes, stage_ms["solve"],
+                 "dependency chain of the 6nc' pivots (FP64 latency), not bytes or flops"),
+                ("backsub_cost_kernel", back_bytes, stage_ms["backsub_retract_cost"], "HBM latency / occupancy")]
+        kernels = []
+        for name, nbytes_, ms_, bound in kern:
+            ach = nbytes_ / (ms_ * 1e-3) / 1e9
+            kernels.append({"kernel": name, "algorithmic_bytes": int(nbytes_), "ms": ms_, "achieved": ach, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": ncu_traffic.get(name), "real_bound": bound})
+        dom = max(kernels, key=lambda kk: kk["ms"])
         iter_bytes = 40 * n_obs_local + 224 * n_pt_local + 16 * n * n + 288 * sc.n_cam
         pairs = float(np.sum((np.diff(sc.pt_ptr).astype(np.float64)) * (np.diff(sc.pt_ptr) + 1) / 2))
         flops_iter = 300.0 * n_obs_local + 216.0 * pairs + n ** 3 / 3.0
+        adds = 36.0 * pairs + 6.0 * n_obs_local
+        elim_s = stage_ms["linearize_eliminate"] * 1e-3
         line = {
             "metric": "observations/sec per LM iteration", "value": value, "unit": "obs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -337,9 +358,15 @@ def run_ours(args):
                                "ms_per_step": 1e3 * e2e_full_s / args.steps,
                                "path": "as e2e, plus the observation arrays (pt_ptr, obs_cam, obs_uv) re-uploaded every step"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "linearize_eliminate_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes": int(elim_bytes), "kernel_ms": stage_ms["linearize_eliminate"]},
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "algorithmic_bytes": dom["algorithmic_bytes"], "kernel_ms": dom["ms"],
+                         "note": "dominant kernel by time; its real bound: " + dom["real_bound"]},
+            "roofline_kernels": kernels,
+            "l2_reduction_roofline": {"kernel": "linearize_eliminate_kernel", "fp64_adds": adds,
+                                      "achieved_adds_per_s": adds / elim_s, "peak_adds_per_s": 5.75e11,
+                                      "frac": adds / elim_s / 5.75e11,
+                                      "peak_source": "tools/microbench/bulk_issue_bench.cu + red_bench.cu on this pool's B200"},
             "iteration_roofline": {"algorithmic_bytes": int(iter_bytes), "achieved_GBs": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9,
                                    "frac_of_hbm_peak": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
                                    "fp64_flops": flops_iter, "fp64_tflops": flops_iter / (total_ms / args.steps * 1e-3) / 1e12},
