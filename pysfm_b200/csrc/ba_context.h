@@ -54,7 +54,7 @@ struct Context {
   double* dC = nullptr;     // [ld]        reduced solution
   double* Adense = nullptr; // [ld*ld + ld] dense lower-triangular copy + rhs, factored in place
   double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
-  unsigned int* solve_flags = nullptr;    // [T*T + T] tile / x_k ready flags (epoch valued)
+  unsigned int* solve_flags = nullptr;    // [T*T + 10T] tile / x_k / y_k / Linv row-block ready flags (epoch valued)
   unsigned int* solve_tickets = nullptr;  // [2] task tickets of the dataflow solver
   unsigned long long* solve_trace = nullptr;  // debug timeline (BA_SOLVE_TRACE builds only)
   unsigned int solve_epoch = 0;

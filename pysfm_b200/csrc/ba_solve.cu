@@ -79,6 +79,11 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -106,6 +111,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
     if (g.trace && threadIdx.x == 0) g.trace[(size_t)(rec) * 8 + (slot)] = (v);    \
   } while (0)
 __device__ long long g_sweep_clk[64];
+__device__ unsigned long long g_dbg_time[256];
+#define BA_GT(idx, cond)                                                           \
+  do {                                                                             \
+    if (cond) {                                                                    \
+      unsigned long long gt__;                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                     \
+      g_dbg_time[(idx)] = gt__;                                                    \
+    }                                                                              \
+  } while (0)
 #define BA_CLK(idx)                                                                \
   do {                                                                             \
     if (t == 0 && tid == 224) g_sweep_clk[(idx)] = clock64();                      \
@@ -124,6 +138,7 @@ __device__ long long g_sweep_clk[64];
     }                                                                              \
   } while (0)
 #else
+#define BA_GT(idx, cond) do { } while (0)
 #define BA_CLK(idx) do { } while (0)
 #define BA_CLK0(idx) do { } while (0)
 #define BA_CLK_DEP(idx, dep) do { } while (0)
@@ -138,7 +153,7 @@ struct CholArgs {
   double* __restrict__ rhs;       // [ld] b -> y (forward substitution)
   double* __restrict__ x;         // [ld] solution
   double* __restrict__ LinvT;     // [T][NB*NB]  LinvT[m*NB + c] = (L_jj^{-1})[c][m]
-  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready
+  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready
   unsigned int* __restrict__ tickets; // [0] tile tasks, [1] back-substitution tasks
   double* __restrict__ status;    // set to 1 on a non-positive pivot
   int ld, T;
@@ -277,76 +292,135 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   const int R0 = 32 * (wid & 1), C0 = 16 * (wid >> 1);
   const int T = g.T;
   const size_t ld = (size_t)g.ld;
-  const int ntasks = T * (T + 1) / 2;
+  const int ntasks = 1 + T * (T - 1) / 2;   // chain task C_0, then per column one chain + the panels below
   const unsigned int epoch = g.epoch;
 
   // ======================================= factorisation ===================================
+  // Ticket order:  C_0;  then per column j = 0 .. T-2:  C_{j+1}, (j+2, j), ..., (T-1, j).
+  //   panel task (i, j), i >= j + 2:  L_ij = (A_ij - sum_{k<j} L_ik L_jk^T) Linv_jj^T
+  //   chain task C_j:  the panel tile (j, j-1) AND the diagonal tile (j, j) in one task, so that
+  //                    L_{j,j-1} goes from the tensor pipe straight into the last update of the
+  //                    diagonal tile without a global-memory round trip and a flag hop.
+  // Both kinds consume Linv_jj ROW BLOCK BY ROW BLOCK while the chain task that owns column j is
+  // still sweeping: rows 8cb .. 8cb+7 of Linv give columns 8cb .. 8cb+7 of L_ij, and (chain
+  // tasks) each finished column block is folded into the diagonal tile at once.  When the sweep
+  // of column j ends, the next chain task is one block (~1 us) away from starting its own sweep.
+  unsigned int* const yflag = g.flags + (size_t)T * T + T;
+  unsigned int* const rowflag = g.flags + (size_t)T * T + 2 * T;
+  const int Tm = T - 1;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_task = (int)atomicAdd(&g.tickets[0], 1u);
     __syncthreads();
     const int t = s_task;
     if (t >= ntasks) break;
-    // column-major enumeration of the lower triangle: column j holds T - j tasks
-    int j = 0, rem = t;
-    {
-      const double Tf = (double)T + 0.5;
-      j = (int)(Tf - sqrt(Tf * Tf - 2.0 * (double)t));
-      if (j < 0) j = 0;
-      if (j > T - 1) j = T - 1;
-      while (j > 0 && (size_t)j * T - (size_t)j * (j - 1) / 2 > (size_t)t) --j;
-      while ((size_t)(j + 1) * T - (size_t)(j + 1) * j / 2 <= (size_t)t) ++j;
-      rem = t - (int)((size_t)j * T - (size_t)j * (j - 1) / 2);
+    bool chain = true;
+    int j = 0;          // chain: diagonal tile index;  panel: column
+    int pi = 0, pj = 0; // the panel tile (pi, pj) of this task (chain: (j, j - 1))
+    if (t > 0) {
+      // column-major enumeration over columns 0 .. T-2, column jc holding T-1-jc tasks
+      const int tt = t - 1;
+      const double Tf = (double)Tm + 0.5;
+      int jc = (int)(Tf - sqrt(Tf * Tf - 2.0 * (double)tt));
+      if (jc < 0) jc = 0;
+      if (jc > Tm - 1) jc = Tm - 1;
+      while (jc > 0 && (size_t)jc * Tm - (size_t)jc * (jc - 1) / 2 > (size_t)tt) --jc;
+      while ((size_t)(jc + 1) * Tm - (size_t)(jc + 1) * jc / 2 <= (size_t)tt) ++jc;
+      const int rem = tt - (int)((size_t)jc * Tm - (size_t)jc * (jc - 1) / 2);
+      chain = (rem == 0);
+      j = chain ? jc + 1 : jc;
+      pi = jc + 1 + rem;
+      pj = jc;
     }
-    const int i = j + rem;
-    const bool diag = (i == j);
-    BA_TRACE_SET(t, 0, ((unsigned long long)i << 32) | (unsigned)j);
+    const bool has_panel = t > 0;
+    BA_TRACE_SET(t, 0, ((unsigned long long)(chain ? j : pi) << 32) | (unsigned)(chain ? j : pj));
     BA_TRACE_SET(t, 1, (unsigned long long)blockIdx.x);
     BA_TRACE(t, 2);   // task grabbed
 
-    const double* Aij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
-    unsigned int* const yflag = g.flags + (size_t)T * T + T;
-
-    if (diag) {
-      // ================================ diagonal task ==========================================
-      // W = A_jj - sum_k L_jk L_jk^T, lower triangle only, as row-block-owned 8x8 tiles.  The
-      // original A_jj is fetched first so that its latency hides behind the k loop.
-      const int r = wid;
-      RowTiles W;
+    // ---- original tiles first: their latency hides behind the k loop --------------------------
+    const int r = wid;   // row block owned in the diagonal tile
+    Frag acc;            // panel tile  A_{pi,pj} - sum_k L_{pi,k} L_{pj,k}^T   (warp tile R0, C0)
+    RowTiles W;          // diagonal tile A_jj - sum_k L_jk L_jk^T, lower triangle, row-block owned
+    acc.zero();
+    if (has_panel) {
+      const double* Ap = g.A + (size_t)(pj * NB) * ld + (size_t)pi * NB;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
+            acc.v[mi][ni][e] = __ldcg(Ap + (size_t)cc * ld + rr);
+          }
+    }
+    double bacc = 0.0, rhs_j = 0.0;   // tid < NB: sum_k (L_jk y_k)[tid], b_j
+#pragma unroll
+    for (int c = 0; c < 8; ++c) W.t[c][0] = W.t[c][1] = 0.0;
+    if (chain) {
+      const double* Ajj = g.A + (size_t)(j * NB) * ld + (size_t)j * NB;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int row = 8 * r + gq, col = 8 * c + 2 * t4 + e;
           const int hi = row > col ? row : col, lo = row > col ? col : row;
-          W.t[c][e] = (c <= r) ? __ldcg(Aij + (size_t)lo * ld + hi) : 0.0;
+          if (c <= r) W.t[c][e] = __ldcg(Ajj + (size_t)lo * ld + hi);
         }
-      double bacc = 0.0;  // tid < NB: sum_k (L_jk y_k)[tid]
-      const double rhs_j = (tid < NB) ? __ldcg(g.rhs + j * NB + tid) : 0.0;   // b_j, fetched early
-      double* const LT = g.LinvT + (size_t)j * NB * NB;
-      auto issue = [&](int k) {
-        stage_tile(buf + (size_t)(2 * (k & 1)) * kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
-        cp_async_commit();
-      };
-      if (j > 0) {
-        wait_flag(&g.flags[(size_t)j * T + 0], epoch);
-        wait_flag(&yflag[0], epoch);
+      if (tid < NB) rhs_j = __ldcg(g.rhs + j * NB + tid);
+    }
+
+    // ---- k loop over the finished columns k < pj:  P = L_{pi,k}, Q = L_{pj,k} ------------------
+    auto issue = [&](int k) {
+      double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+      stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)pi * NB, ld);
+      stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)pj * NB, ld);
+      cp_async_commit();
+    };
+    auto wait_k = [&](int k) {
+      wait_flag(&g.flags[(size_t)pi * T + k], epoch);
+      wait_flag(&g.flags[(size_t)pj * T + k], epoch);
+      if (chain) wait_flag(&yflag[k], epoch);
+    };
+    // thread 0: are the operands of step k out already?  (non-blocking; relaxed loads + fence)
+    auto ready_k = [&](int k) -> bool {
+      const unsigned int f0 = ld_relaxed(&g.flags[(size_t)pi * T + k]);
+      const unsigned int f1 = ld_relaxed(&g.flags[(size_t)pj * T + k]);
+      const unsigned int f2 = chain ? ld_relaxed(&yflag[k]) : epoch;
+      const bool ok = f0 == epoch && f1 == epoch && f2 == epoch;
+      if (ok) __threadfence();
+      return ok;
+    };
+    // The tiles of step k+1 are prefetched while step k computes ONLY if they are already
+    // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
+    // of step k+1 before computing step k put a whole extra tile product behind every late
+    // operand -- the last operand of a chain task always is.)
+    int issued = 0;
+    for (int k = 0; k < pj; ++k) {
+      if (issued == k) {
+        wait_k(k);
         __syncthreads();
-        issue(0);
+        issue(k);
+        issued = k + 1;
       }
-      for (int k = 0; k < j; ++k) {
-        if (k + 1 < j) {
-          wait_flag(&g.flags[(size_t)j * T + k + 1], epoch);
-          wait_flag(&yflag[k + 1], epoch);
-          __syncthreads();
+      if (k + 1 < pj) {
+        if (tid == 0) s_task = ready_k(k + 1) ? 1 : 0;
+        __syncthreads();
+        if (s_task) {
           issue(k + 1);
+          issued = k + 2;
           cp_async_wait<1>();
         } else {
           cp_async_wait<0>();
         }
-        if (tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
-        __syncthreads();
-        const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+      } else {
+        cp_async_wait<0>();
+      }
+      if (chain && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
+      __syncthreads();
+      const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+      tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
+      if (chain) {
         diag_rows_dmma(W, P, r, lane);
         if (tid < NB) {
           double s = 0.0;
@@ -354,10 +428,131 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
           bacc += s;
         }
-        __syncthreads();
       }
-      BA_TRACE(t, 3);   // k loop done
+      __syncthreads();
+    }
+    BA_TRACE(t, 3);   // k loop done
 
+    double* const Cs = buf;                       // [m][row] = C[row][m]      (A operand)
+    double* const Bs = buf + kTileDoubles;        // [m][c]   = Linv_pj[c][m]  (B operand), filled block by block
+    double* const Ls = buf + 2 * kTileDoubles;    // [m][row] = L_{pi,pj}[row][m]
+    if (has_panel) {
+      // ---- progressive panel:  L[:, 8cb..8cb+7] = C[:, 0..8cb+7] Linv[8cb..8cb+7, 0..8cb+7]^T ----
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
+            Cs[cc * LDT + rr] = acc.v[mi][ni][e];
+          }
+      const double* LTp = g.LinvT + (size_t)pj * NB * NB;
+      double* Lout = g.A + (size_t)(pj * NB) * ld + (size_t)pi * NB;
+      const unsigned int* rf = rowflag + (size_t)pj * 8;
+      // thread tid fetches the 16-byte chunk (m = tid >> 2, columns 8cb + 2 (tid & 3) ..) of a block
+      auto fetch_block = [&](int cb) {
+        if (tid < 4 * (8 * cb + 8))
+          cp_async16(Bs + (tid >> 2) * LDT + 8 * cb + 2 * (tid & 3), LTp + (size_t)(tid >> 2) * NB + 8 * cb + 2 * (tid & 3));
+      };
+      // Row blocks are taken in GROUPS [cb, ce): whatever the owner of column pj has already
+      // published is processed in one go (one fetch, one pipelined batch of DMMAs), so a task
+      // that arrives late catches up at tensor-pipe speed instead of one block per round trip.
+      int cb = 0;
+#pragma unroll 1
+      while (cb < 8) {
+        if (tid == 0) {
+          // one round trip: all flags at once (relaxed, independent loads) ...
+          unsigned int f[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+          int e = cb;
+          bool run = true;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q >= cb) {
+              run = run && (f[q] == epoch);
+              if (run) e = q + 1;
+            }
+          // ... and a fence as the acquire; only when nothing is ready yet, spin on the next block
+          if (e == cb) {
+            e = cb + 1;
+            while (ld_acquire(rf + cb) != epoch) __nanosleep(20);
+          } else {
+            while (ld_acquire(rf + e - 1) != epoch) { }   // already set: one more round trip, no membar
+          }
+          s_task = e;
+        }
+        __syncthreads();
+        const int ce = s_task;
+        BA_GT(16 + 32 * (t - 52) + 4 * cb + 0, (t == 52 || t == 53) && tid == 0);
+#ifdef BA_SOLVE_TRACE
+        if ((t == 52 || t == 53) && tid == 0) g_dbg_time[80 + 8 * (t - 52) + cb] = ce;
+#endif
+        for (int q = cb; q < ce; ++q) fetch_block(q);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
+        BA_GT(16 + 32 * (t - 52) + 4 * cb + 1, (t == 52 || t == 53) && tid == 0);
+        // warp w: the 8x8 tiles rows 8w.., column blocks cb .. ce-1.  Tile q contracts over the
+        // 8 (q + 1) columns of Linv that are non-zero in its rows: two interleaved accumulator
+        // chains, operands of the next step loaded before the DMMAs of this one are issued, no
+        // predication anywhere near the tensor instructions.
+#pragma unroll 1
+        for (int q = cb; q < ce; ++q) {
+          const double* pa = Cs + t4 * LDT + 8 * wid + gq;
+          const double* pb = Bs + t4 * LDT + 8 * q + gq;
+          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+          double a0 = pa[0], a1 = pa[4 * LDT], b0 = pb[0], b1 = pb[4 * LDT];
+          const int kend = 8 * q + 8;
+#pragma unroll 1
+          for (int m0 = 8; m0 < kend; m0 += 8) {
+            const double na0 = pa[m0 * LDT], na1 = pa[(m0 + 4) * LDT];
+            const double nb0 = pb[m0 * LDT], nb1 = pb[(m0 + 4) * LDT];
+            dmma884(e0, e1, a0, b0);
+            dmma884(f0, f1, a1, b1);
+            a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+          }
+          dmma884(e0, e1, a0, b0);
+          dmma884(f0, f1, a1, b1);
+          e0 += f0; e1 += f1;
+          const int col = 8 * q + 2 * t4, row = 8 * wid + gq;
+          if (chain) {
+            Ls[col * LDT + row] = e0;
+            Ls[(col + 1) * LDT + row] = e1;
+          }
+          Lout[(size_t)col * ld + row] = e0;
+          Lout[(size_t)(col + 1) * ld + row] = e1;
+        }
+        BA_GT(16 + 32 * (t - 52) + 4 * cb + 2, (t == 52 || t == 53) && tid == 0);
+        if (chain) {
+          __syncthreads();   // column blocks cb .. ce-1 of L_{j,j-1} are complete in Ls
+          const double* q0 = Ls + t4 * LDT + gq;
+          for (int m0 = 8 * cb; m0 < 8 * ce; m0 += 4) {
+            const double* q = q0 + m0 * LDT;
+            const double av = -q[8 * r];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
+          }
+        }
+        BA_GT(16 + 32 * (t - 52) + 4 * cb + 3, (t == 52 || t == 53) && tid == 0);
+        cb = ce;
+      }
+      // tile (pi, pj) of L is out.  Only warp 7 pays for the fence (its stores and, through the
+      // barrier, everybody else's): in a chain task the other warps go straight on to the sweep,
+      // whose first Gauss-Jordan step is longer than the fence.
+      __syncthreads();
+      if (wid == 7) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
+      }
+      BA_TRACE(t, 6);   // panel part done
+    }
+
+    if (chain) {
+      double* const LT = g.LinvT + (size_t)j * NB * NB;
       // ---- blocked sweep: 8 panel steps of 8 pivots ------------------------------------------
       // Step pb:  warp 0 (whose row block holds no trailing tiles) factors the 8x8 pivot block
       // D = W(pb,pb) by Gauss-Jordan in registers into Linv_d = L_d^{-1} and shares it through
@@ -489,6 +684,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
         __syncthreads();   // (Y) Lp, Mp in place; Wcol / Mrow / Ld free again
         BA_CLK(pb * 4 + 3);
+        if (r == pb) {
+          // rows 8 pb .. 8 pb + 7 of L_jj^{-1} are final and this warp has nothing left to do in
+          // the sweep: make them visible and let the consumers of this column start (the fence
+          // is kept out of the X..Y window, where the whole CTA would wait for it)
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
+          BA_GT(pb, t == 36 && lane == 0);
+        }
         if (r > pb) {
           const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];
           if (pb + 1 < 8) {
@@ -545,12 +749,24 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           LTs[(e >> 6) * LDT + (e & 63)] = v;
           LT[e] = v;
         }
+        __threadfence();
+      }
+      // forward substitution: y_j = Linv (b_j - sum_{k<j} L_jk y_k); the k = j-1 term comes from
+      // the panel tile this task produced itself (still in Ls)
+      if (j > 0) {
+        wait_flag(&yflag[j - 1], epoch);
+        __syncthreads();
+        if (tid < NB) yk[tid] = __ldcg(g.rhs + (j - 1) * NB + tid);
+        __syncthreads();
+        if (tid < NB) {
+          double s = 0.0;
+#pragma unroll 8
+          for (int m = 0; m < NB; ++m) s += Ls[m * LDT + tid] * yk[m];
+          bacc += s;
+        }
       }
       if (tid < NB) tvec[tid] = rhs_j - bacc;
-      __threadfence();
       __syncthreads();
-      if (tid == 0) st_release(&g.flags[(size_t)j * T + j], epoch);   // L_jj^{-1} is out: panels may go
-      // forward substitution: y_j = Linv (b_j - sum_k L_jk y_k);  thread r: sum_m LTs[m][r] t[m]
       // (the 8x8 tiles of LTs above the block diagonal were never written: stop at the diagonal tile)
       if (tid < NB) {
         double s = 0.0;
@@ -562,81 +778,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
       __syncthreads();
       if (tid == 0) st_release(&yflag[j], epoch);
-    } else {
-      // ================================ panel task =============================================
-      // C = A_ij - sum_k L_ik L_jk^T  (A_ij fetched up front),  then  L_ij = C Linv_jj^T
-      Frag acc;
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            acc.v[mi][ni][e] = __ldcg(Aij + (size_t)c * ld + r);
-          }
-      auto issue = [&](int k) {
-        double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
-        stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)i * NB, ld);
-        stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)j * NB, ld);
-        cp_async_commit();
-      };
-      if (j > 0) {
-        wait_flag(&g.flags[(size_t)i * T + 0], epoch);
-        wait_flag(&g.flags[(size_t)j * T + 0], epoch);
-        __syncthreads();
-        issue(0);
-      }
-      for (int k = 0; k < j; ++k) {
-        if (k + 1 < j) {
-          wait_flag(&g.flags[(size_t)i * T + k + 1], epoch);
-          wait_flag(&g.flags[(size_t)j * T + k + 1], epoch);
-          __syncthreads();
-          issue(k + 1);
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
-        }
-        __syncthreads();
-        const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
-        tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
-        __syncthreads();
-      }
-      BA_TRACE(t, 3);   // k loop done
-      double* Cs = buf;                  // [m][r] = C[r][m]
-      double* Bs = buf + kTileDoubles;   // [m][c] = Linv[c][m]
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            Cs[c * LDT + r] = acc.v[mi][ni][e];
-          }
-      wait_flag(&g.flags[(size_t)j * T + j], epoch);
-      __syncthreads();
-      BA_TRACE(t, 4);   // diagonal inverse available
-      stage_tile(Bs, g.LinvT + (size_t)j * NB * NB, NB);
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncthreads();
-      Frag out;
-      out.zero();
-      tile_dmma<false>(out, Cs, Bs, R0, C0, lane);
-      double* Lij = g.A + (size_t)(j * NB) * ld + (size_t)i * NB;
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = R0 + 8 * mi + gq, c = C0 + 8 * ni + 2 * t4 + e;
-            Lij[(size_t)c * ld + r] = out.v[mi][ni][e];
-          }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release(&g.flags[(size_t)i * T + j], epoch);
     }
     BA_TRACE(t, 5);   // published
   }
@@ -660,7 +801,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
     if (tid == 0) {
-      while (ld_acquire(&g.flags[(size_t)k * T + k]) != epoch) __nanosleep(20);          // L_kk^{-1}
+      while (ld_acquire(&g.flags[(size_t)T * T + 2 * T + (size_t)k * 8 + 7]) != epoch) __nanosleep(20);   // L_kk^{-1}
       while (ld_acquire(&g.flags[(size_t)T * T + T + k]) != epoch) __nanosleep(20);      // y_k
       for (int i = T - 1; i > k; --i)
         while (ld_acquire(&g.flags[(size_t)i * T + k]) != epoch) __nanosleep(20);        // tiles (i, k)
@@ -745,7 +886,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
 #ifdef BA_SOLVE_TRACE
   g.trace = c.solve_trace;
 #endif
-  const int ntasks = T * (T + 1) / 2;
+  const int ntasks = 1 + T * (T - 1) / 2;
   int grid = ntasks < c.num_sms ? ntasks : c.num_sms;   // 1 CTA / SM (128 KB smem): all co-resident
   chol_dataflow_kernel<<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
   c.launches += 1;

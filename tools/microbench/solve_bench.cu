@@ -40,11 +40,11 @@ int main(int argc, char** argv) {
   ba::Context c;
   c.n_opt_cam = nc; c.n_sys = n; c.ld = ld; c.sys_len = sys_len;
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0); c.num_sms = sms;
-  const int ntasks = T * (T + 1) / 2;
+  const int ntasks = 1 + T * (T - 1) / 2;
   CK(cudaMalloc(&c.sys, sys_len * 8)); CK(cudaMemcpy(c.sys, packed.data(), sys_len * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c.Adense, ((size_t)ld * ld + ld) * 8));
   CK(cudaMalloc(&c.LinvT, (size_t)T * 4096 * 8)); CK(cudaMemset(c.LinvT, 0, (size_t)T * 4096 * 8));
-  CK(cudaMalloc(&c.solve_flags, ((size_t)T * T + 2 * T) * 4)); CK(cudaMemset(c.solve_flags, 0, ((size_t)T * T + 2 * T) * 4));
+  CK(cudaMalloc(&c.solve_flags, ((size_t)T * T + 10 * T) * 4)); CK(cudaMemset(c.solve_flags, 0, ((size_t)T * T + 10 * T) * 4));
   CK(cudaMalloc(&c.solve_tickets, 8));
   CK(cudaMalloc(&c.dC, ld * 8));
   CK(cudaMalloc(&c.cam_mask, ld));
@@ -78,14 +78,30 @@ int main(int argc, char** argv) {
   unsigned long long t0 = ~0ull;
   for (int t = 0; t < ntasks + T; ++t) if (tr[(size_t)t * 8 + 2]) t0 = std::min(t0, tr[(size_t)t * 8 + 2]);
   const int show = argc > 3 ? atoi(argv[3]) : 60;
-  printf("task  (i,j)  cta  grab_us  kloop_us  fact/inv_us  publish_us\n");
+  printf("task  (i,j)  cta  grab_us  kloop_us  panel_done_us  sweep_done_us  publish_us   (chain tasks show (j,j))\n");
   for (int t = 0; t < ntasks + T; ++t) {
     const unsigned long long* r = &tr[(size_t)t * 8];
     const int i = (int)(r[0] >> 32), j = (int)(r[0] & 0xffffffffu);
-    const bool interesting = t >= ntasks || i == j || i == j + 1 || i == T - 1;
+    const bool interesting = t >= ntasks || i == j || i == j + 2 || i == T - 1;
     if (!interesting || (t > show && t < ntasks - 8)) continue;
-    printf("%4d (%3d,%3d) %4llu %9.2f %9.2f %9.2f %9.2f\n", t, i, j, r[1], (r[2] - t0) * 1e-3, (r[3] - t0) * 1e-3,
-           r[4] ? (r[4] - t0) * 1e-3 : 0.0, (r[5] - t0) * 1e-3);
+    printf("%4d (%3d,%3d) %4llu %9.2f %9.2f %9.2f %9.2f %9.2f\n", t, i, j, r[1], (r[2] - t0) * 1e-3, (r[3] - t0) * 1e-3,
+           r[6] ? (r[6] - t0) * 1e-3 : 0.0, r[4] ? (r[4] - t0) * 1e-3 : 0.0, (r[5] - t0) * 1e-3);
+  }
+  {
+    unsigned long long dt[256];
+    CK(cudaMemcpyFromSymbol(dt, ba::g_dbg_time, sizeof dt));
+    printf("row-block flags of C_3 (task 36) released at (us):");
+    for (int q = 0; q < 8; ++q) printf(" %.2f", (dt[q] - t0) * 1e-3);
+    for (int tk = 0; tk < 2; ++tk) {
+      printf("\nconsumer task %d groups: ", tk + 52);
+      for (int q = 0; q < 8; ++q) {
+        const unsigned long long* d = dt + 16 + 32 * tk + 4 * q;
+        if (!d[0]) continue;
+        printf("\n   cb=%d ce=%llu: polled %.2f fetched %.2f panel %.2f update %.2f", q, dt[80 + 8 * tk + q], (d[0] - t0) * 1e-3, (d[1] - t0) * 1e-3,
+               (d[2] - t0) * 1e-3, (d[3] - t0) * 1e-3);
+      }
+    }
+    printf("\n");
   }
   long long clk[64];
   CK(cudaMemcpyFromSymbol(clk, ba::g_sweep_clk, sizeof clk));
