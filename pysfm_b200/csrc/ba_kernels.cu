@@ -21,6 +21,9 @@
 
 namespace ba {
 
+// Loads of the observation / point streams use __ldcs (evict-first, no L1 allocation): the few KB
+// of L1 the shared-memory carve-out leaves are kept for the camera arrays, which every
+// observation gathers from and which otherwise cost an L2 round trip under reduction load.
 // ------------------------------------------------------------------------------------------
 // shared argument block (passed by value in kernel parameter space)
 struct ObsArgs {
@@ -142,17 +145,17 @@ linearize_eliminate_kernel(const ElimArgs A) {
   const int stride = gridDim.x * warps_per_cta;
   int pt = blockIdx.x * warps_per_cta + wid;
   int cur_beg = 0, cur_end = 0, nxt_beg = 0, nxt_end = 0;
-  if (pt < o.n_pt) { cur_beg = o.pt_ptr[pt]; cur_end = o.pt_ptr[pt + 1]; }
-  if (pt + stride < o.n_pt) { nxt_beg = o.pt_ptr[pt + stride]; nxt_end = o.pt_ptr[pt + stride + 1]; }
+  if (pt < o.n_pt) { cur_beg = __ldcs(o.pt_ptr + (pt)); cur_end = __ldcs(o.pt_ptr + (pt + 1)); }
+  if (pt + stride < o.n_pt) { nxt_beg = __ldcs(o.pt_ptr + (pt + stride)); nxt_end = __ldcs(o.pt_ptr + (pt + stride + 1)); }
   int pf_cam = 0, pf_ptslot = -1;
   double2 pf_uv = make_double2(0.0, 0.0);
   double pf_x0 = 0.0, pf_x1 = 0.0, pf_x2 = 0.0;
   if (pt < o.n_pt) {
-    pf_x0 = o.pts[3 * pt]; pf_x1 = o.pts[3 * pt + 1]; pf_x2 = o.pts[3 * pt + 2];
-    pf_ptslot = o.pt_slot[pt];
+    pf_x0 = __ldcs(o.pts + (3 * pt)); pf_x1 = __ldcs(o.pts + (3 * pt + 1)); pf_x2 = __ldcs(o.pts + (3 * pt + 2));
+    pf_ptslot = __ldcs(o.pt_slot + (pt));
     if (lane < cur_end - cur_beg) {
-      pf_cam = o.obs_cam[cur_beg + lane];
-      pf_uv = reinterpret_cast<const double2*>(o.obs_uv)[cur_beg + lane];
+      pf_cam = __ldcs(o.obs_cam + (cur_beg + lane));
+      pf_uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (cur_beg + lane));
     }
   }
   for (; pt < o.n_pt; pt += stride) {
@@ -165,13 +168,13 @@ linearize_eliminate_kernel(const ElimArgs A) {
     {   // advance the pipeline
       const int p1 = pt + stride, p2 = pt + 2 * stride;
       cur_beg = nxt_beg; cur_end = nxt_end;
-      if (p2 < o.n_pt) { nxt_beg = o.pt_ptr[p2]; nxt_end = o.pt_ptr[p2 + 1]; }
+      if (p2 < o.n_pt) { nxt_beg = __ldcs(o.pt_ptr + (p2)); nxt_end = __ldcs(o.pt_ptr + (p2 + 1)); }
       if (p1 < o.n_pt) {
-        pf_x0 = o.pts[3 * p1]; pf_x1 = o.pts[3 * p1 + 1]; pf_x2 = o.pts[3 * p1 + 2];
-        pf_ptslot = o.pt_slot[p1];
+        pf_x0 = __ldcs(o.pts + (3 * p1)); pf_x1 = __ldcs(o.pts + (3 * p1 + 1)); pf_x2 = __ldcs(o.pts + (3 * p1 + 2));
+        pf_ptslot = __ldcs(o.pt_slot + (p1));
         if (lane < cur_end - cur_beg) {
-          pf_cam = o.obs_cam[cur_beg + lane];
-          pf_uv = reinterpret_cast<const double2*>(o.obs_uv)[cur_beg + lane];
+          pf_cam = __ldcs(o.obs_cam + (cur_beg + lane));
+          pf_uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (cur_beg + lane));
         }
       }
     }
@@ -180,8 +183,8 @@ linearize_eliminate_kernel(const ElimArgs A) {
     // ---- phase A: lanes over observations ------------------------------------------------
     for (int a = lane; a < k; a += 32) {
       const int ob = beg + a;
-      const int cam = (a < 32) ? cam0 : o.obs_cam[ob];
-      const double2 uv = (a < 32) ? uv0 : reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      const int cam = (a < 32) ? cam0 : __ldcs(o.obs_cam + (ob));
+      const double2 uv = (a < 32) ? uv0 : __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
       const int slot = o.cam_slot[cam];
       double r[2], Jc[12], Jp[6];
       observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
@@ -395,13 +398,13 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
   for (int base = (blockIdx.x * warps_per_cta + wid) * NG; base < o.n_pt; base += gridDim.x * warps_per_cta * NG) {
     const int pt = base + sub;
     const bool live = pt < o.n_pt;
-    const int beg = live ? o.pt_ptr[pt] : 0;
-    const int k = live ? o.pt_ptr[pt + 1] - beg : 0;
+    const int beg = live ? __ldcs(o.pt_ptr + (pt)) : 0;
+    const int k = live ? __ldcs(o.pt_ptr + (pt + 1)) - beg : 0;
     double x[3] = {0.0, 0.0, 0.0};
     int pslot = -1;
     if (live) {
-      x[0] = o.pts[3 * pt]; x[1] = o.pts[3 * pt + 1]; x[2] = o.pts[3 * pt + 2];
-      pslot = o.pt_slot[pt];
+      x[0] = __ldcs(o.pts + (3 * pt)); x[1] = __ldcs(o.pts + (3 * pt + 1)); x[2] = __ldcs(o.pts + (3 * pt + 2));
+      pslot = __ldcs(o.pt_slot + (pt));
     }
     double xc[3] = {x[0], x[1], x[2]};
     // sum_j W_j^T dC_j  ==  sum_j Jp_j^T (Jc_j dC_j)
@@ -409,10 +412,10 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
     if (pslot >= 0) {
       for (int a = gl; a < k; a += G) {
         const int ob = beg + a;
-        const int cam = o.obs_cam[ob];
+        const int cam = __ldcs(o.obs_cam + (ob));
         const int slot = o.cam_slot[cam];
         if (slot < 0) continue;
-        const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+        const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
         double r[2], Jc[12], Jp[6];
         observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
         const double* d = A.dC + 6 * slot;
@@ -448,9 +451,9 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
     if (pslot >= 0) {
       for (int a = gl; a < k; a += G) {
         const int ob = beg + a;
-        const int cam = o.obs_cam[ob];
+        const int cam = __ldcs(o.obs_cam + (ob));
         if (o.cam_slot[cam] < 0) continue;
-        const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+        const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
         double r[2];
         residual_only(o.intr, o.model, A.cand_R + 9 * cam, A.cand_t + 3 * cam, xc, uv.x, uv.y, r);
         cost_acc += r[0] * r[0] + r[1] * r[1];
@@ -475,15 +478,15 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs A) {
   const int warps_per_cta = blockDim.x >> 5;
   double cost_acc = 0.0;
   for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
-    if (o.pt_slot[pt] < 0) continue;
-    const int beg = o.pt_ptr[pt];
-    const int k = o.pt_ptr[pt + 1] - beg;
-    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    if (__ldcs(o.pt_slot + (pt)) < 0) continue;
+    const int beg = __ldcs(o.pt_ptr + (pt));
+    const int k = __ldcs(o.pt_ptr + (pt + 1)) - beg;
+    const double x[3] = {__ldcs(o.pts + (3 * pt)), __ldcs(o.pts + (3 * pt + 1)), __ldcs(o.pts + (3 * pt + 2))};
     for (int a = lane; a < k; a += 32) {
       const int ob = beg + a;
-      const int cam = o.obs_cam[ob];
+      const int cam = __ldcs(o.obs_cam + (ob));
       if (o.cam_slot[cam] < 0) continue;
-      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
       double r[2];
       residual_only(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r);
       cost_acc += r[0] * r[0] + r[1] * r[1];
@@ -506,13 +509,13 @@ __global__ void __launch_bounds__(256) eval_observations_kernel(const EvalArgs A
   const int wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
-    const int beg = o.pt_ptr[pt];
-    const int k = o.pt_ptr[pt + 1] - beg;
-    const double x[3] = {o.pts[3 * pt], o.pts[3 * pt + 1], o.pts[3 * pt + 2]};
+    const int beg = __ldcs(o.pt_ptr + (pt));
+    const int k = __ldcs(o.pt_ptr + (pt + 1)) - beg;
+    const double x[3] = {__ldcs(o.pts + (3 * pt)), __ldcs(o.pts + (3 * pt + 1)), __ldcs(o.pts + (3 * pt + 2))};
     for (int a = lane; a < k; a += 32) {
       const int ob = beg + a;
-      const int cam = o.obs_cam[ob];
-      const double2 uv = reinterpret_cast<const double2*>(o.obs_uv)[ob];
+      const int cam = __ldcs(o.obs_cam + (ob));
+      const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
       double r[2], Jc[12], Jp[6];
       observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
       A.r[2 * ob] = r[0]; A.r[2 * ob + 1] = r[1];

@@ -14,13 +14,13 @@ b = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"
 ba = BundleAdjuster(b, device="cuda:0", verbose=False)
 p = ba._problem
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
-for name, extra in (("full", 0), ("no bulk issue", 16), ("no phase D", 32), ("full", 0)):
+for name, extra in (("full", 0), ("no bulk issue", 16), ("no phase D", 32), ("phases A+B(V,bP) only", -2), ("full", 0)):
     ts = []
     for it in range(8):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        p.linearize_eliminate(10.0, 1e-5, _lib.BA_WANT_SCHUR | extra)
+        p.linearize_eliminate(10.0, 1e-5, (_lib.BA_WANT_SCHUR | extra) if extra >= 0 else 0)
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
