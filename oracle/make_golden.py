@@ -242,6 +242,48 @@ def main():
                        [3.0, 0.1, -0.2], [1e-4, 1e-4, -1e-4]])
         save("so3_exp", ms=ms, Rs=np.array([rlie.SO3.exp(m) for m in ms]))
 
+    if not args.only_oleg:
+        # 10. sliding-window driver (window_slam.py:17-67): 7 cameras x 110 tracks, windows of 4
+        import window_slam as rws
+        import geometry as rgeo
+        from pysfm_b200 import synthetic
+        a = synthetic.make_arrays(7, 110, 7, seed=23, noise=0.5, init_sigma=0.02)
+        nc, nt = len(a["Rs"]), len(a["pts"])
+        msm = np.zeros((nc, nt, 2))
+        mask = np.zeros((nc, nt), bool)
+        msm[a["obs_cam"], a["obs_track"]] = a["obs_uv"]
+        mask[a["obs_cam"], a["obs_track"]] = True
+        b = rbundle.Bundle.FromArrays(a["K"], a["Rs"], a["ts"], a["pts"], msm, mask)
+        d = scene_arrays(b)
+        with quiet():
+            rws.run(b, 4)          # the reference's run() returns nothing: it leaves the result in ...
+        # ... nothing reachable either, so re-run the same loop body through the reference classes
+        from copy import deepcopy
+        cur = rbundle.Bundle.FromArrays(a["K"], a["Rs"], a["ts"], a["pts"], msm, mask)
+        win_costs = []
+        with quiet():
+            for i in range(0, nc - 4 + 1):
+                prev = deepcopy(cur)
+                ba = rba.BundleAdjuster()
+                ba.set_bundle(cur, camera_ids=range(i, i + 4), track_ids=range(100))
+                ba.optimize()
+                cur = ba.bundle
+                win_costs.append(np.asarray(ba.costs, dtype=np.float64))
+                if i + 4 < len(cur.cameras):
+                    rgeo.propagate_pose_update_inplace(prev.cameras[i], cur.cameras[i], cur.cameras[i])
+        d['win_size'] = np.int64(4)
+        d['win_Rs'] = np.array([c.R for c in cur.cameras])
+        d['win_ts'] = np.array([c.t for c in cur.cameras])
+        d['win_pts'] = np.asarray(cur.reconstruction).copy()
+        d['win_final_costs'] = np.array([c[-1] for c in win_costs])
+        d['win_num_costs'] = np.array([len(c) for c in win_costs])
+        # geometry.py known answers
+        R0, t0, R1, t1 = d['Rs'][0], d['ts'][0], d['Rs'][1], d['ts'][1]
+        Rr, tr = rgeo.relative_pose(R0, t0, R1, t1)
+        Rp, tp = rgeo.propagate_pose_update(R0, t0, R1, t1, d['Rs'][2], d['ts'][2])
+        d['geo_rel_R'], d['geo_rel_t'], d['geo_prop_R'], d['geo_prop_t'] = Rr, tr, Rp, tp
+        save("window_slam", **d)
+
     if args.oleg > 0:
         import bundle_io as rio
         droot = os.path.join(refshim.REFERENCE_ROOT, "data", "oleg_synthetic")

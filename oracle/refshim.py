@@ -32,9 +32,10 @@ _SHIMMED = {
     "algebra", "lie", "sensor_model", "triangulate", "bundle", "optimize", "schur",
     "bundle_adjuster", "bundle_io", "numpy_test", "finite_differences",
     "bundle_unittest", "bundle_adjuster_unittest", "finite_differences_unittest",
-    "test_bundle", "synthetic_data", "sequence", "geometry",
+    "test_bundle", "synthetic_data", "sequence", "geometry", "window_slam",
 }
-_STUBBED = {"draw_bundle"}  # matplotlib-only; absent in this image
+# matplotlib-only modules (absent in this image): every attribute is a no-op callable
+_STUBBED = {"draw_bundle", "draw_bundle_pca", "matplotlib", "matplotlib.pyplot"}
 
 
 def available():
@@ -127,6 +128,7 @@ class _StubLoader(importlib.abc.Loader):
     def create_module(self, spec):
         mod = types.ModuleType(spec.name)
         mod.__getattr__ = lambda name: (lambda *a, **k: None)
+        mod.__path__ = []   # lets "import matplotlib.pyplot" treat the stub as a package
         return mod
 
     def exec_module(self, module):

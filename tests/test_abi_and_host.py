@@ -180,3 +180,18 @@ def test_so3_exp_host_matches_reference_golden():
     g = load_golden("so3_exp")
     for m, R in zip(g["ms"], g["Rs"]):
         assert np.max(np.abs(lie.SO3.exp(m) - R)) < 1e-15
+
+
+def test_geometry_matches_reference_golden():
+    """pysfm_b200.geometry (host side of the sliding-window driver) against geometry.py:5-25."""
+    from conftest import load_golden, relerr
+    from pysfm_b200 import geometry
+    g = load_golden("window_slam")
+    R0, t0, R1, t1 = g["Rs"][0], g["ts"][0], g["Rs"][1], g["ts"][1]
+    Rr, tr = geometry.relative_pose(R0, t0, R1, t1)
+    assert relerr(Rr, g["geo_rel_R"]) < 1e-14 and relerr(tr, g["geo_rel_t"]) < 1e-14
+    Rp, tp = geometry.propagate_pose_update(R0, t0, R1, t1, g["Rs"][2], g["ts"][2])
+    assert relerr(Rp, g["geo_prop_R"]) < 1e-14 and relerr(tp, g["geo_prop_t"]) < 1e-14
+    for f in (geometry.rotation_xy, geometry.rotation_xz, geometry.rotation_yz):
+        R = f(0.3)
+        assert abs(np.linalg.det(R) - 1.0) < 1e-14 and relerr(R.dot(R.T), np.eye(3)) < 1e-14
