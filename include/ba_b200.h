@@ -167,6 +167,11 @@ int ba_get_array(ba_handle h, int which, double* dst_host, size_t count, void* s
 int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt_host,
                void* stream);
 
+/* Linear (algebraic) multi-view triangulation of EVERY bound point from the current cameras
+ * and the measurements (triangulate.algebraic_lsq, triangulate.py:6-18, as called by
+ * Bundle.triangulate_all, bundle.py:313-321); overwrites the bound state points [n_pt][3]. */
+int ba_triangulate(ba_handle h, void* stream);
+
 /* Overwrite the reduced solution dC from a HOST array [n_opt_cam][6] -- lets the staged
  * Python API call backsubstitute(dC) with a caller-supplied camera update (:316). */
 int ba_set_solution(ba_handle h, const double* dC_host, void* stream);

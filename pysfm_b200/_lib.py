@@ -51,6 +51,7 @@ SIGNATURES = {
     "ba_eval_observations": (ctypes.c_int, [_vp, _vp]),
     "ba_get_array": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
     "ba_retract": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "ba_triangulate": (ctypes.c_int, [_vp, _vp]),
     "ba_set_solution": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_sync": (ctypes.c_int, [_vp, _vp]),
     "ba_launch_count": (ctypes.c_longlong, [_vp]),

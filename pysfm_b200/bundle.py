@@ -387,5 +387,23 @@ class Bundle(object):
         return _tri.algebraic_lsq(self.K, [self.cameras[i].R for i in ids], [self.cameras[i].t for i in ids],
                                   [track.measurements[i] for i in ids])
 
-    def triangulate_all(self):
-        self.reconstruction = np.array([self.triangulate(track) for track in self.tracks])
+    def triangulate_all(self, device=None):
+        """Replace every point by its linear triangulation (bundle.py:313-321).  With `device`
+        (e.g. "cuda:0") all tracks are triangulated by one kernel launch (ba_triangulate);
+        without it the reference's per-track host loop runs (numpy mirror in triangulate.py)."""
+        if device is None:
+            self.reconstruction = np.array([self.triangulate(track) for track in self.tracks])
+            return
+        from . import scene as _scene
+        cams = list(range(len(self.cameras)))
+        trks = list(range(self.num_tracks()))
+        if np.shape(self.reconstruction) != (len(trks), 3):
+            self.reconstruction = np.zeros((len(trks), 3))
+        packed = _scene.pack_scene(self, cams, trks, range(len(cams)), range(len(trks)))
+        prob = _scene.DeviceProblem(packed, device)
+        try:
+            prob.triangulate()
+            _, _, x = prob.download("state")
+        finally:
+            prob.close()
+        self.reconstruction = np.array(x, dtype=np.float64)

@@ -332,6 +332,14 @@ int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt
   return BA_OK;
 }
 
+int ba_triangulate(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h)) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, ba::launch_triangulate(*h, (cudaStream_t)stream));
+  return BA_OK;
+}
+
 int ba_set_solution(ba_handle h, const double* dC_host, void* stream) {
   if (!h || !dC_host) return BA_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;

@@ -83,6 +83,7 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st);
 cudaError_t launch_cost(Context& c, cudaStream_t st);
 cudaError_t launch_eval_observations(Context& c, cudaStream_t st);
 cudaError_t launch_retract(Context& c, bool have_cam, bool have_pt, cudaStream_t st);
+cudaError_t launch_triangulate(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
 
 }  // namespace ba

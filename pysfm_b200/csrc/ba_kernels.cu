@@ -528,6 +528,61 @@ __global__ void __launch_bounds__(256) eval_observations_kernel(const EvalArgs A
 }
 
 // ------------------------------------------------------------------------------------------
+// Linear multi-view triangulation of every point (triangulate.py:6-18, Bundle.triangulate_all
+// bundle.py:313-321): the two algebraic constraints per observation
+//     (K0 - u K2)(R x + t) = 0,   (K1 - v K2)(R x + t) = 0
+// are accumulated as 3x3 normal equations by a warp per point and solved with the symmetric
+// pseudo-inverse (eigen-directions below 1e-13 of the largest eigenvalue are dropped, which is
+// numpy.linalg.lstsq's minimum-norm answer for a track that is seen by a single camera).
+struct TriArgs {
+  ObsArgs o;
+  double* __restrict__ out;   // [n_pt][3]
+};
+
+__global__ void __launch_bounds__(256) triangulate_kernel(const TriArgs A) {
+  const ObsArgs& o = A.o;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const double* K = o.intr.K;
+  for (int pt = blockIdx.x * warps_per_cta + wid; pt < o.n_pt; pt += gridDim.x * warps_per_cta) {
+    const int beg = __ldcs(o.pt_ptr + pt);
+    const int k = __ldcs(o.pt_ptr + pt + 1) - beg;
+    double M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+    for (int a = lane; a < k; a += 32) {
+      const int ob = beg + a;
+      const int cam = __ldcs(o.obs_cam + ob);
+      const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob);
+      const double* R = o.cam_R + 9 * cam;
+      const double* t = o.cam_t + 3 * cam;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double m = e ? uv.y : uv.x;
+        const double c0 = K[3 * e] - m * K[6], c1 = K[3 * e + 1] - m * K[7], c2 = K[3 * e + 2] - m * K[8];
+        const double r0 = c0 * R[0] + c1 * R[3] + c2 * R[6];
+        const double r1 = c0 * R[1] + c1 * R[4] + c2 * R[7];
+        const double r2 = c0 * R[2] + c1 * R[5] + c2 * R[8];
+        const double bb = -(c0 * t[0] + c1 * t[1] + c2 * t[2]);
+        M[0] += r0 * r0; M[1] += r0 * r1; M[2] += r0 * r2;
+        M[3] += r1 * r1; M[4] += r1 * r2; M[5] += r2 * r2;
+        v[0] += r0 * bb; v[1] += r1 * bb; v[2] += r2 * bb;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) M[i] = warp_sum(M[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+      const double Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
+      double Mi[9];
+      sym3_pinv(Mf, 1e-13, Mi);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) A.out[3 * pt + i] = Mi[3 * i] * v[0] + Mi[3 * i + 1] * v[1] + Mi[3 * i + 2] * v[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side launchers
 static ObsArgs make_obs_args(const Context& c, const ParamSet& ps) {
   ObsArgs o;
@@ -636,6 +691,16 @@ cudaError_t launch_eval_observations(Context& c, cudaStream_t st) {
   A.r = c.obs_r; A.Jc = c.obs_Jc; A.Jp = c.obs_Jp;
   const int grid = point_grid(c, 8, 8);
   eval_observations_kernel<<<grid, 256, 0, st>>>(A);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_triangulate(Context& c, cudaStream_t st) {
+  TriArgs A;
+  A.o = make_obs_args(c, c.state);
+  A.out = c.state.pts;
+  const int grid = point_grid(c, 8, 8);
+  triangulate_kernel<<<grid, 256, 0, st>>>(A);
   c.launches += 1;
   return cudaGetLastError();
 }

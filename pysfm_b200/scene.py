@@ -271,6 +271,10 @@ class DeviceProblem(object):
     def eval_observations(self):
         self._chk(self.lib.ba_eval_observations(self.h, self._stream()), "ba_eval_observations")
 
+    def triangulate(self):
+        """Algebraic triangulation of every point from the current cameras (overwrites state points)."""
+        self._chk(self.lib.ba_triangulate(self.h, self._stream()), "ba_triangulate")
+
     def accept(self):
         self._chk(self.lib.ba_accept(self.h), "ba_accept")
         self.cur = 1 - self.cur

@@ -267,3 +267,33 @@ def test_window_slam_matches_reference(cuda_device):
     assert relerr(out.Rs(), g["win_Rs"]) < 1e-6
     assert relerr(out.ts(), g["win_ts"]) < 1e-6
     assert relerr(out.reconstruction, g["win_pts"]) < 1e-6
+
+
+def test_triangulate_all_on_device(cuda_device):
+    """ba_triangulate against (a) the points the unmodified reference triangulated for
+    data/oleg_synthetic (bundle_io.load + triangulate_all, kept in the golden fixture) and
+    (b) numpy.linalg.lstsq per track on a ragged synthetic scene incl. a single-view track
+    (minimum-norm answer)."""
+    from pysfm_b200 import synthetic, triangulate
+    from pysfm_b200.bundle import Bundle
+    g = load_golden("oleg_synthetic")
+    b = golden_bundle(g)
+    ref = b.reconstruction.copy()
+    b.reconstruction = np.zeros_like(ref)
+    b.triangulate_all(device=cuda_device)
+    assert relerr(b.reconstruction, ref) < 1e-9
+    # ragged scene: 9 cameras, tracks of 1..9 views
+    a = synthetic.make_arrays(9, 60, 9, seed=41, noise=0.3)
+    rs = np.random.RandomState(5)
+    keep = np.ones(len(a["obs_cam"]), bool)
+    for j in range(60):
+        idx = np.where(a["obs_track"] == j)[0]
+        nkeep = 1 if j == 0 else rs.randint(2, 10)
+        keep[idx[rs.permutation(9)[nkeep:]]] = False
+    oc, ot, uv = a["obs_cam"][keep], a["obs_track"][keep], a["obs_uv"][keep]
+    b = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], np.zeros((60, 3)), oc, ot, uv)
+    b.triangulate_all(device=cuda_device)
+    for j in range(60):
+        sel = np.where(ot == j)[0]
+        x = triangulate.algebraic_lsq(a["K"], a["Rs"][oc[sel]], a["ts"][oc[sel]], uv[sel])
+        assert relerr(b.reconstruction[j], x) < (1e-6 if len(sel) < 3 else 1e-9), (j, len(sel))
