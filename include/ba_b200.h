@@ -154,6 +154,24 @@ int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_hos
  * side can all-reduce the two costs when points are sharded over ranks. */
 int ba_scalars_ptr(ba_handle h, double** scalars_dev);
 
+/* ---- points sharded over the GPUs of ONE node --------------------------------
+ * Peer-memory collectives over NVLink: each rank (one handle per GPU/process) exports one device
+ * buffer through CUDA IPC and maps the buffers of its peers.
+ *   ba_comm_create    allocates the buffer, returns its 64-byte IPC handle and REBINDS the system
+ *                     buffer of the handle to it (ba_comm_system_ptr gives the device pointer);
+ *   ba_comm_connect   takes the handles of all ranks (world x 64 bytes, rank order; exchanged by
+ *                     the host side, e.g. torch.distributed.all_gather_object);
+ *   ba_allreduce_system  ONE kernel: barrier, each rank sums its slice of all ranks' packed systems
+ *                     (rank order) and pushes it to every rank, barrier; the next ba_solve factors
+ *                     the reduced copy.  Replaces the NCCL all-reduce of the reduced camera system;
+ *   ba_allreduce_costs   sums {cost, candidate cost} over the ranks into every rank's scalars.
+ * All ranks must issue the same sequence of these two calls. */
+int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_out64);
+int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all);
+int ba_comm_system_ptr(ba_handle h, double** sys_dev);
+int ba_allreduce_system(ba_handle h, void* stream);
+int ba_allreduce_costs(ba_handle h, void* stream);
+
 /* Per-observation residuals and Jacobians of the current state (bundle.py:251, :255-277),
  * for Bundle.residuals()/Jresiduals() and stage-wise parity checks. */
 int ba_eval_observations(ba_handle h, void* stream);

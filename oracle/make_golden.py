@@ -243,6 +243,13 @@ def main():
         save("so3_exp", ms=ms, Rs=np.array([rlie.SO3.exp(m) for m in ms]))
 
     if not args.only_oleg:
+        # 11. the Cauchy-robustified fixture through the whole LM loop (sensor_model.py:37-72 in optimize)
+        b = rbu.create_test_bundle()
+        d = scene_arrays(b)
+        d.update(run_stages(rba, b, 10.0, tag="d10_"))
+        d.update(run_optimize(rba, b, max_steps=25))
+        save("fixture_cauchy_optimize", **d)
+
         # 10. sliding-window driver (window_slam.py:17-67): 7 cameras x 110 tracks, windows of 4
         import window_slam as rws
         import geometry as rgeo

@@ -48,6 +48,11 @@ SIGNATURES = {
     "ba_trial_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp,
                                      _c_double_p, _c_double_p, _c_int_p, _vp]),
     "ba_scalars_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "ba_comm_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "ba_comm_connect": (ctypes.c_int, [_vp, _vp]),
+    "ba_comm_system_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "ba_allreduce_system": (ctypes.c_int, [_vp, _vp]),
+    "ba_allreduce_costs": (ctypes.c_int, [_vp, _vp]),
     "ba_eval_observations": (ctypes.c_int, [_vp, _vp]),
     "ba_get_array": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
     "ba_retract": (ctypes.c_int, [_vp, _vp, _vp, _vp]),

@@ -125,6 +125,15 @@ class BundleAdjuster(object):
         self._packed = packed.shard(self._rank, self._world)
         self._problem = _scene.DeviceProblem(self._packed, self._device)
         self._scalars_t = self._problem.scalars_tensor() if self._world > 1 else None
+        if self._world > 1 and self._peer_comm_wanted():
+            import torch.distributed as dist
+
+            def gather(b):
+                parts = [None] * self._world
+                dist.all_gather_object(parts, b)
+                return parts
+            self._problem.enable_peer_comm(self._rank, self._world, gather)
+            dist.barrier()
         self._damp_factor = 1.0
         self._blocks = {}
         self._say('Configured a bundle adjuster for %d cameras, %d tracks' %
@@ -159,15 +168,30 @@ class BundleAdjuster(object):
 
     # ------------------------------------------------------------------------------------------
     # collectives (only when points are sharded)
+    def _peer_comm_wanted(self):
+        """Peer-memory collectives (ba_comm.cu) when all ranks sit on one node (<= 8 GPUs); the
+        NCCL all-reduce otherwise, or when PYSFM_B200_COLLECTIVE=nccl asks for it."""
+        import os
+        if os.environ.get("PYSFM_B200_COLLECTIVE", "peer").lower() == "nccl":
+            return False
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", self._world))
+        return self._world <= 8 and local == self._world
+
     def _allreduce_system(self):
         if self._world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._problem.sys)
+            if self._problem.peer_comm:
+                self._problem.allreduce_system()
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self._problem.sys)
 
     def _allreduce_costs(self):
         if self._world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._scalars_t[:2])
+            if self._problem.peer_comm:
+                self._problem.allreduce_costs()
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self._scalars_t[:2])
 
     # ------------------------------------------------------------------------------------------
     def _trial(self, damping, cam_param_mask=None):

@@ -134,7 +134,70 @@ int ba_destroy(ba_handle h) {
                   h->scalars, h->Adense, h->LinvT, h->solve_flags, h->solve_tickets};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (int p = 0; p < ba::kMaxPeers; ++p)
+    if (h->comm_peer[p] && p != h->comm_rank) cudaIpcCloseMemHandle(h->comm_peer[p]);
+  if (h->comm_buf) cudaFree(h->comm_buf);
+  if (h->comm_done) cudaFree(h->comm_done);
   delete h;
+  return BA_OK;
+}
+
+// ---- peer-memory collectives (ba_comm.cu) -----------------------------------------------------
+int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_out) {
+  if (!h || !ipc_handle_out || world < 2 || world > ba::kMaxPeers || rank < 0 || rank >= world)
+    return BA_ERR_BAD_ARGUMENT;
+  if (h->comm_buf) { h->last_error = "ba_comm_create called twice"; return BA_ERR_BAD_ARGUMENT; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, dev_alloc(&h->comm_buf, ba::comm_doubles(h->sys_len)));
+  BA_CUDA(h, dev_alloc(&h->comm_done, (size_t)1));
+  cudaIpcMemHandle_t mh;
+  BA_CUDA(h, cudaIpcGetMemHandle(&mh, h->comm_buf));
+  memcpy(ipc_handle_out, &mh, sizeof mh);
+  h->comm_rank = rank;
+  h->comm_world = world;
+  h->comm_peer[rank] = h->comm_buf;
+  h->sys = h->comm_buf;   // the rank's own contribution lives at the head of the exported buffer
+  BA_CUDA(h, cudaDeviceSynchronize());
+  return BA_OK;
+}
+
+int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all) {
+  if (!h || !ipc_handles_all || !h->comm_buf) return BA_ERR_BAD_ARGUMENT;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  for (int p = 0; p < h->comm_world; ++p) {
+    if (p == h->comm_rank) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, ipc_handles_all + (size_t)p * sizeof mh, sizeof mh);
+    void* ptr = nullptr;
+    BA_CUDA(h, cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->comm_peer[p] = static_cast<double*>(ptr);
+  }
+  return BA_OK;
+}
+
+int ba_comm_system_ptr(ba_handle h, double** sys_dev) {
+  if (!h || !sys_dev || !h->comm_buf) return BA_ERR_BAD_ARGUMENT;
+  *sys_dev = h->comm_buf;
+  return BA_OK;
+}
+
+int ba_allreduce_system(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!h->comm_buf) return BA_ERR_NOT_BOUND;
+  for (int p = 0; p < h->comm_world; ++p)
+    if (!h->comm_peer[p]) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, ba::launch_peer_allreduce_system(*h, (cudaStream_t)stream));
+  h->sys_reduced = true;
+  return BA_OK;
+}
+
+int ba_allreduce_costs(ba_handle h, void* stream) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  if (!h->comm_buf) return BA_ERR_NOT_BOUND;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_CUDA(h, ba::launch_peer_allreduce_costs(*h, (cudaStream_t)stream));
   return BA_OK;
 }
 
@@ -188,6 +251,7 @@ int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int f
   int rc = ensure_track_len(*h, st);
   if (rc != BA_OK) return rc;
   if ((flags & BA_WANT_BLOCKS) && !h->W) BA_CUDA(h, dev_alloc(&h->W, (size_t)h->n_obs * 18));
+  if (flags & BA_WANT_SCHUR) h->sys_reduced = false;   // a fresh local contribution
   cudaError_t e = ba::launch_linearize_eliminate(*h, damping, pinv_rcond, flags, st);
   if (e == cudaErrorInvalidValue) {
     h->last_error = "track too long for the shared-memory elimination tile";

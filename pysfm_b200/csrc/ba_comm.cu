@@ -1,0 +1,151 @@
+// Peer-memory collectives for points sharded over the GPUs of ONE node.
+//
+// Every rank owns one IPC-exported device buffer:
+//     contrib [sys_len]   its own packed reduced system (the elimination kernel reduces into it)
+//     reduced [sys_len]   the all-reduced system (peers push their slices here; the solver reads it)
+//     costs   [world][2]  {cost, candidate cost} of every rank (pushed by the ranks)
+//     flags   [3][world]  arrival flags of the three barriers (epoch valued, never reset)
+// and maps the buffers of all peers (NVLink 5 / NVSwitch: every peer at full bandwidth).
+//
+//   peer_allreduce_system_kernel   ONE kernel per LM iteration instead of an NCCL all-reduce:
+//       barrier A (everybody's elimination is complete)  ->  rank r sums slice r of all ranks'
+//       contributions over NVLink, in rank order, and pushes the result into EVERY rank's
+//       `reduced`  ->  barrier B (all slices have landed).  2 (N-1)/N |sys| bytes per rank cross
+//       the links, the same as a ring all-reduce, but in two hops and one launch; each element is
+//       reduced by exactly one rank, so all ranks factor bit-identical systems.
+//   peer_allreduce_costs_kernel    the two cost scalars, summed in rank order on every rank.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_context.h"
+
+namespace ba {
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 ld_peer2(const double* p) {   // never cached: peers rewrite it every iteration
+  double2 v;
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+struct PeerArgs {
+  double* base[kMaxPeers];   // comm buffer of every rank (own rank included), peer-mapped
+  int world, rank;
+  size_t sys_len;            // doubles
+  size_t lo, hi;             // this rank's slice [lo, hi) of the packed system (even bounds)
+  unsigned int epoch;
+  unsigned int* done;        // local CTA counter (last-CTA-done)
+};
+
+__device__ __forceinline__ double* contrib_of(double* base) { return base; }
+__device__ __forceinline__ double* reduced_of(double* base, size_t sys_len) { return base + comm_pad(sys_len); }
+__device__ __forceinline__ double* costs_of(double* base, size_t sys_len) { return base + 2 * comm_pad(sys_len); }
+__device__ __forceinline__ unsigned int* flags_of(double* base, size_t sys_len) {
+  return reinterpret_cast<unsigned int*>(base + 2 * comm_pad(sys_len) + 2 * kMaxPeers);
+}
+
+// signal barrier `which` to every rank, then wait until every rank has signalled us
+__device__ __forceinline__ void peer_barrier(const PeerArgs& g, int which, int lane_in_block) {
+  if (lane_in_block < g.world) {
+    __threadfence_system();
+    st_release_sys(flags_of(g.base[lane_in_block], g.sys_len) + which * kMaxPeers + g.rank, g.epoch);
+    const unsigned int* mine = flags_of(g.base[g.rank], g.sys_len) + which * kMaxPeers + lane_in_block;
+    while ((int)(ld_acquire_sys(mine) - g.epoch) < 0) __nanosleep(40);
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_system_kernel(const PeerArgs g) {
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  // ---- barrier A: every rank's contribution is complete (its elimination kernel precedes this
+  // launch in its stream); CTA 0 signals, every CTA waits on the local flags -------------------
+  if (blockIdx.x == 0 && tid < g.world) {
+    __threadfence_system();
+    st_release_sys(flags_of(g.base[tid], g.sys_len) + 0 * kMaxPeers + g.rank, g.epoch);
+  }
+  if (tid < g.world) {
+    const unsigned int* mine = flags_of(g.base[g.rank], g.sys_len) + 0 * kMaxPeers + tid;
+    while ((int)(ld_acquire_sys(mine) - g.epoch) < 0) __nanosleep(40);
+  }
+  __syncthreads();
+  // ---- reduce my slice over all ranks (rank order), push it to everybody -----------------------
+  const size_t n2 = (g.hi - g.lo) / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = g.lo + 2 * i;
+    double2 s = ld_peer2(contrib_of(g.base[0]) + e);
+    for (int p = 1; p < g.world; ++p) {
+      const double2 v = ld_peer2(contrib_of(g.base[p]) + e);
+      s.x += v.x; s.y += v.y;
+    }
+    for (int p = 0; p < g.world; ++p) *reinterpret_cast<double2*>(reduced_of(g.base[p], g.sys_len) + e) = s;
+  }
+  // ---- barrier B: the last CTA of this rank tells everybody that its slice has landed, then
+  // waits for everybody else's ----------------------------------------------------------------
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(g.done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (tid == 0) *g.done = 0u;
+    peer_barrier(g, 1, tid);
+  }
+}
+
+__global__ void peer_allreduce_costs_kernel(const PeerArgs g, Scalars* sc) {
+  const int tid = threadIdx.x;
+  if (tid < g.world) {
+    double* c = costs_of(g.base[tid], g.sys_len) + 2 * g.rank;
+    c[0] = sc->cost;
+    c[1] = sc->cand_cost;
+  }
+  peer_barrier(g, 2, tid);
+  __syncwarp();
+  if (tid == 0) {
+    const volatile double* c = costs_of(g.base[g.rank], g.sys_len);
+    double a = 0.0, b = 0.0;
+    for (int p = 0; p < g.world; ++p) { a += c[2 * p]; b += c[2 * p + 1]; }
+    sc->cost = a;
+    sc->cand_cost = b;
+  }
+}
+
+static PeerArgs make_peer_args(Context& c) {
+  PeerArgs g;
+  for (int p = 0; p < kMaxPeers; ++p) g.base[p] = p < c.comm_world ? c.comm_peer[p] : nullptr;
+  g.world = c.comm_world; g.rank = c.comm_rank; g.sys_len = c.sys_len;
+  size_t chunk = (c.sys_len + c.comm_world - 1) / c.comm_world;
+  chunk = (chunk + 1) & ~(size_t)1;
+  const size_t padded = (c.sys_len + 1) & ~(size_t)1;   // the buffer is padded to an even length
+  g.lo = chunk * c.comm_rank < padded ? chunk * c.comm_rank : padded;
+  g.hi = g.lo + chunk < padded ? g.lo + chunk : padded;
+  g.epoch = ++c.comm_epoch;
+  g.done = c.comm_done;
+  return g;
+}
+
+cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st) {
+  const PeerArgs g = make_peer_args(c);
+  const size_t n2 = (g.hi - g.lo) / 2;
+  int grid = (int)((n2 + 255) / 256);
+  if (grid > c.num_sms) grid = c.num_sms;
+  if (grid < 1) grid = 1;
+  peer_allreduce_system_kernel<<<grid, 256, 0, st>>>(g);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st) {
+  const PeerArgs g = make_peer_args(c);
+  peer_allreduce_costs_kernel<<<1, 32, 0, st>>>(g, c.scalars);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace ba

@@ -8,6 +8,12 @@
 namespace ba {
 
 constexpr int kSolveTile = 64;  // Cholesky tile; the reduced system is padded to a multiple
+constexpr int kMaxPeers = 8;    // GPUs of one node (ba_comm.cu)
+
+// doubles reserved per section of the peer-visible comm buffer (even, so that sections stay
+// 16-byte aligned): [contrib | reduced | costs 2*kMaxPeers | flags 3*kMaxPeers u32]
+__host__ __device__ inline size_t comm_pad(size_t sys_len) { return (sys_len + 2 + 31) & ~(size_t)31; }
+inline size_t comm_doubles(size_t sys_len) { return 2 * comm_pad(sys_len) + 2 * kMaxPeers + (3 * kMaxPeers + 1) / 2 + 2; }
 
 struct ParamSet {   // caller-owned device arrays
   double* cam_R = nullptr;  // [n_cam][9]
@@ -72,6 +78,14 @@ struct Context {
   Scalars* scalars = nullptr;
   int partials_cap = 0;
 
+  // peer-memory collectives (points sharded over the GPUs of one node)
+  int comm_world = 0, comm_rank = 0;
+  double* comm_buf = nullptr;               // own IPC-exported buffer (== comm_peer[comm_rank])
+  double* comm_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned int* comm_done = nullptr;        // last-CTA-done counter of the all-reduce kernel
+  unsigned int comm_epoch = 0;
+  bool sys_reduced = false;                 // the solver reads the all-reduced copy
+
   long long launches = 0;
   std::string last_error;
 };
@@ -84,6 +98,8 @@ cudaError_t launch_cost(Context& c, cudaStream_t st);
 cudaError_t launch_eval_observations(Context& c, cudaStream_t st);
 cudaError_t launch_retract(Context& c, bool have_cam, bool have_pt, cudaStream_t st);
 cudaError_t launch_triangulate(Context& c, cudaStream_t st);
+cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st);
+cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
 
 }  // namespace ba

@@ -865,7 +865,9 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   cudaError_t e;
   if ((e = cudaMemsetAsync(&c.scalars->status, 0, sizeof(double), st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(c.solve_tickets, 0, 2 * sizeof(unsigned int), st)) != cudaSuccess) return e;
-  expand_system_kernel<<<ld, 256, 0, st>>>(c.sys, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask,
+  // sharded problems: factor the all-reduced copy the peers pushed (ba_comm.cu), not the local contribution
+  const double* packed = (c.sys_reduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
+  expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask,
                                            c.Adense, c.Adense + (size_t)ld * ld);
   c.launches += 1;
   if (!c.solve_attr_set) {

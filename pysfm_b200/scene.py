@@ -202,6 +202,7 @@ class DeviceProblem(object):
         sp = ctypes.c_void_p()
         self._chk(self.lib.ba_scalars_ptr(h, ctypes.byref(sp)), "ba_scalars_ptr")
         self._scalars_ptr = sp.value
+        self.peer_comm = False
 
     # -- plumbing --------------------------------------------------------------------------
     def _chk(self, rc, what):
@@ -343,6 +344,35 @@ class DeviceProblem(object):
         assert (not t.is_cuda) and t.dtype == self.torch.float64 and t.is_contiguous() and t.numel() == count, \
             'expected a contiguous float64 CPU tensor of %d elements' % count
         return ctypes.c_void_p(t.data_ptr())
+
+    # -- peer-memory collectives (points sharded over the GPUs of one node) ------------------------
+    def enable_peer_comm(self, rank, world, all_gather):
+        """Export this rank's comm buffer, exchange the IPC handles with `all_gather(bytes) ->
+        [bytes per rank]`, map the peers.  Afterwards `self.sys` views the library-owned buffer."""
+        torch = self.torch
+        mine = (ctypes.c_ubyte * 64)()
+        self._chk(self.lib.ba_comm_create(self.h, int(rank), int(world), ctypes.cast(mine, ctypes.c_void_p)), "ba_comm_create")
+        handles = all_gather(bytes(mine))
+        assert len(handles) == world and all(len(b) == 64 for b in handles)
+        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._chk(self.lib.ba_comm_connect(self.h, ctypes.cast(blob, ctypes.c_void_p)), "ba_comm_connect")
+        sp = ctypes.c_void_p()
+        self._chk(self.lib.ba_comm_system_ptr(self.h, ctypes.byref(sp)), "ba_comm_system_ptr")
+
+        class _Wrap(object):
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (max(self.sys_len, 2),), "typestr": "<f8", "data": (sp.value, False),
+                                      "version": 2}
+        self._sys_keepalive = w
+        self.sys = torch.as_tensor(w, device=self.device)
+        self.peer_comm = True
+
+    def allreduce_system(self):
+        self._chk(self.lib.ba_allreduce_system(self.h, self._stream()), "ba_allreduce_system")
+
+    def allreduce_costs(self):
+        self._chk(self.lib.ba_allreduce_costs(self.h, self._stream()), "ba_allreduce_costs")
 
     def read_scalars(self):
         cost, cand = ctypes.c_double(), ctypes.c_double()

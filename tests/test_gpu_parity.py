@@ -22,6 +22,7 @@ STAGE_CASES = [
     ("fixture_rank_deficient", "d0_"), ("fixture_rank_deficient", "dtiny_"), ("fixture_rank_deficient", "d3_"),
     ("planar_optimize", "d10_"),
     ("config1_synthetic", "d10_"), ("config1_synthetic", "dsmall_"),
+    ("fixture_cauchy_optimize", "d10_"),
 ]
 
 
@@ -102,7 +103,7 @@ def test_reference_unit_tests_dense_known_answers(cuda_device):
 
 
 @pytest.mark.parametrize("name,max_steps", [("fixture_gaussian", 25), ("planar_optimize", 50),
-                                            ("config1_synthetic", 25)])
+                                            ("config1_synthetic", 25), ("fixture_cauchy_optimize", 25)])
 def test_optimize_matches_reference_trace(name, max_steps, cuda_device):
     from pysfm_b200.bundle_adjuster import BundleAdjuster
     g = load_golden(name)
@@ -113,6 +114,11 @@ def test_optimize_matches_reference_trace(name, max_steps, cuda_device):
     assert len(ba.costs) == len(ref)
     assert ba.num_steps == int(g["opt_num_steps"])
     assert ba.converged == bool(g["opt_converged"])
+    if name == "fixture_cauchy_optimize":
+        # lambda reaches 1e-23 on a nearly gauge-singular reduced system: see the oracle test
+        assert relerr(np.array(ba.costs)[:12], ref[:12]) < 1e-9
+        assert relerr(np.array(ba.costs), ref) < 1e-4
+        return
     assert relerr(np.array(ba.costs), ref) < 1e-6
     assert relerr(ba.bundle.Rs(), g["opt_Rs"]) < 1e-6
     assert relerr(ba.bundle.ts(), g["opt_ts"]) < 1e-6

@@ -23,6 +23,7 @@ STAGE_CASES = [
     ("fixture_rank_deficient", "d0_"), ("fixture_rank_deficient", "dtiny_"), ("fixture_rank_deficient", "d3_"),
     ("planar_optimize", "d10_"),
     ("config1_synthetic", "d10_"), ("config1_synthetic", "dsmall_"),
+    ("fixture_cauchy_optimize", "d10_"),
 ]
 
 
@@ -98,7 +99,7 @@ def test_subset_dense_known_answer():
 
 
 @pytest.mark.parametrize("name,max_steps", [("fixture_gaussian", 25), ("planar_optimize", 50),
-                                            ("config1_synthetic", 25)])
+                                            ("config1_synthetic", 25), ("fixture_cauchy_optimize", 25)])
 def test_optimize_trace(name, max_steps):
     g = load_golden(name)
     prefix = [k for k in g if k.endswith("camera_ids")][0][:-len("camera_ids")]
@@ -108,6 +109,13 @@ def test_optimize_trace(name, max_steps):
     assert len(info["costs"]) == len(ref)
     assert info["num_steps"] == int(g["opt_num_steps"])
     assert info["converged"] == bool(g["opt_converged"])
+    if name == "fixture_cauchy_optimize":
+        # 25 accepted steps drive lambda to 1e-23 on a scene whose reduced system is then nearly
+        # gauge-singular: roundoff is amplified step by step (the costs still agree to 1e-5, the
+        # iterates drift along the weakly determined directions).  Tight on the first 12 steps.
+        assert relerr(np.array(info["costs"])[:12], ref[:12]) < 1e-9
+        assert relerr(np.array(info["costs"]), ref) < 1e-5
+        return
     assert relerr(np.array(info["costs"]), ref) < 1e-7
     assert relerr(Pf.R, g["opt_Rs"]) < 1e-6
     assert relerr(Pf.x, g["opt_pts"]) < 1e-6
