@@ -11,7 +11,8 @@ candidate cost), the accept path of bundle_adjuster.py:127-157.
 Workload: BASELINE config 2 (200 cameras / 50,000 points / 500,000 observations, sigma = 1 px)
 per GPU.  With N > 1 ranks the scene has N x 50,000 points over the same 200 cameras (weak
 scaling), points sharded contiguously, the reduced camera system all-reduced over NCCL once
-per step plus an 16-byte cost reduction.
+per step plus an 16-byte cost reduction (ba_comm.cu peer-memory kernels on one node;
+PYSFM_B200_COLLECTIVE=nccl selects the torch.distributed all-reduce instead).
 
 Keys of the JSON line: see the builder contract.  `value` = device-timed throughput with the
 scene resident in HBM; `e2e` = the same iteration driven from HOST buffers (pinned), H2D of
@@ -164,7 +165,9 @@ def workload_config(n):
                         "pixel noise sigma=1.0, GaussianModel(1.), camera 0 fixed, damping=%g" % (
                             CAMS, PTS_PER_GPU * n, PTS_PER_GPU * n * K_OBS, K_OBS, DAMPING),
             "cameras": CAMS, "points": PTS_PER_GPU * n, "observations": PTS_PER_GPU * n * K_OBS,
-            "parallelism": "points sharded over %d rank(s); reduced camera system all-reduced (NCCL)" % n if n > 1
+            "parallelism": ("points sharded over %d rank(s); reduced camera system all-reduced by " % n) +
+            ("torch.distributed (NCCL)" if os.environ.get("PYSFM_B200_COLLECTIVE", "peer").lower() == "nccl"
+             else "ba_comm peer-memory kernels over NVLink") if n > 1
             else "single GPU",
             "l2": "L2 flushed (256 MiB write) before every timed step"}
 
@@ -238,7 +241,7 @@ def run_ours(args):
     # ---- per-stage device times (same stream, CUDA events), L2 flushed before each step ------
     stage_names = ["linearize_eliminate", "allreduce_system", "solve", "backsub_retract_cost"]
     stage_ms = dict((k, 0.0) for k in stage_names)
-    reps = min(args.steps, 10)
+    reps = min(args.steps, 20)
     for _ in range(reps):
         flush.zero_()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -387,7 +390,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -76,15 +76,21 @@ __global__ void __launch_bounds__(256) peer_allreduce_system_kernel(const PeerAr
   }
   __syncthreads();
   // ---- reduce my slice over all ranks (rank order), push it to everybody -----------------------
+  // all peers' loads of an element are in flight together (NVLink round trip ~1 us), then the sum
   const size_t n2 = (g.hi - g.lo) / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < n2; i += (size_t)gridDim.x * blockDim.x) {
     const size_t e = g.lo + 2 * i;
-    double2 s = ld_peer2(contrib_of(g.base[0]) + e);
-    for (int p = 1; p < g.world; ++p) {
-      const double2 v = ld_peer2(contrib_of(g.base[p]) + e);
-      s.x += v.x; s.y += v.y;
-    }
-    for (int p = 0; p < g.world; ++p) *reinterpret_cast<double2*>(reduced_of(g.base[p], g.sys_len) + e) = s;
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < g.world) v[p] = ld_peer2(contrib_of(g.base[p]) + e);
+    double2 s = v[0];
+#pragma unroll
+    for (int p = 1; p < kMaxPeers; ++p)
+      if (p < g.world) { s.x += v[p].x; s.y += v[p].y; }
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < g.world) *reinterpret_cast<double2*>(reduced_of(g.base[p], g.sys_len) + e) = s;
   }
   // ---- barrier B: the last CTA of this rank tells everybody that its slice has landed, then
   // waits for everybody else's ----------------------------------------------------------------
@@ -134,7 +140,7 @@ cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st) {
   const PeerArgs g = make_peer_args(c);
   const size_t n2 = (g.hi - g.lo) / 2;
   int grid = (int)((n2 + 255) / 256);
-  if (grid > c.num_sms) grid = c.num_sms;
+  if (grid > 4 * c.num_sms) grid = 4 * c.num_sms;
   if (grid < 1) grid = 1;
   peer_allreduce_system_kernel<<<grid, 256, 0, st>>>(g);
   c.launches += 1;

@@ -14,6 +14,12 @@ b = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"
 ba = BundleAdjuster(b, device="cuda:0", verbose=False)
 p = ba._problem
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+if len(sys.argv) > 1 and sys.argv[1] == "cudamalloc":
+    # experiment: system buffer in a plain cudaMalloc allocation (as the peer-comm path has it)
+    import ctypes
+    mine = (ctypes.c_ubyte * 64)()
+    p._chk(p.lib.ba_comm_create(p.h, 0, 2, ctypes.cast(mine, ctypes.c_void_p)), "ba_comm_create")
+    print("system buffer rebound to a cudaMalloc allocation")
 for name, extra in (("full", 0), ("no bulk issue", 16), ("no phase D", 32), ("phases A+B(V,bP) only", -2), ("full", 0)):
     ts = []
     for it in range(8):
