@@ -150,6 +150,14 @@ int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_hos
                   const unsigned char* cam_param_mask_host, double* dC_host, double* dP_host,
                   double* cost, double* cand_cost, int* solve_status, void* stream);
 
+/* The same trial with ONE copy in each direction.  in_host = [cam_R 9 n_cam | cam_t 3 n_cam |
+ * pts 3 n_pt] (NULL keeps the device estimate; a single H2D when the bound state arrays are
+ * contiguous in that order, three otherwise); out_host receives
+ * [cost, candidate cost, status (0 / 1 = ill-conditioned), spare | dC ba_system_ld(6 n_opt_cam) |
+ * dP 3 n_pt] in a single D2H. */
+int ba_trial_host_packed(ba_handle h, const double* in_host, double damping, double pinv_rcond,
+                         const unsigned char* cam_param_mask_host, double* out_host, void* stream);
+
 /* Device address of the 4-double scalar record {cost, cand_cost, status, spare} so the host
  * side can all-reduce the two costs when points are sharded over ranks. */
 int ba_scalars_ptr(ba_handle h, double** scalars_dev);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ba_read_scalars": (ctypes.c_int, [_vp, _c_double_p, _c_double_p, _c_int_p, _vp]),
     "ba_trial_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp,
                                      _c_double_p, _c_double_p, _c_int_p, _vp]),
+    "ba_trial_host_packed": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp]),
     "ba_scalars_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "ba_comm_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "ba_comm_connect": (ctypes.c_int, [_vp, _vp]),

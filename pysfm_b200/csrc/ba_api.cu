@@ -106,22 +106,26 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->V, (size_t)n_pt * 9) == cudaSuccess &&
             dev_alloc(&c->U, (size_t)n_cam * 36) == cudaSuccess &&
             dev_alloc(&c->bC, (size_t)n_cam * 6) == cudaSuccess &&
-            dev_alloc(&c->dC, (size_t)c->ld) == cudaSuccess &&
+            dev_alloc(&c->io_out, (size_t)4 + c->ld + (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->Adense, (size_t)c->ld * c->ld + c->ld) == cudaSuccess &&
             dev_alloc(&c->LinvT, T * ba::kSolveTile * ba::kSolveTile) == cudaSuccess &&
             dev_alloc(&c->solve_flags, T * T + 10 * T) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
-            dev_alloc(&c->dP, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->cam_mask, (size_t)c->ld) == cudaSuccess &&
             dev_alloc(&c->partials, (size_t)c->partials_cap) == cudaSuccess &&
             dev_alloc(&c->counters, (size_t)8) == cudaSuccess &&
-            dev_alloc(&c->scalars, (size_t)1) == cudaSuccess;
+            true;
   if (!ok) {
     ba_destroy(c);
     return BA_ERR_CUDA;
   }
+  // results of a trial live in ONE block so that a host-driven trial reads them back in one copy
+  static_assert(sizeof(ba::Scalars) == 4 * sizeof(double), "scalar record is 4 doubles");
+  c->scalars = reinterpret_cast<ba::Scalars*>(c->io_out);
+  c->dC = c->io_out + 4;
+  c->dP = c->io_out + 4 + c->ld;
   *out = c;
   return BA_OK;
 }
@@ -129,9 +133,9 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
 int ba_destroy(ba_handle h) {
   if (!h) return BA_OK;
   cudaSetDevice(h->device);
-  void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->dC, h->dP, h->obs_r, h->obs_Jc,
+  void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->scalars, h->Adense, h->LinvT, h->solve_flags, h->solve_tickets};
+                  h->Adense, h->LinvT, h->solve_flags, h->solve_tickets};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
@@ -333,6 +337,31 @@ int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_hos
   if (dP_host)
     BA_CUDA(h, cudaMemcpyAsync(dP_host, h->dP, (size_t)h->n_pt * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   return ba_read_scalars(h, cost, cand_cost, solve_status, stream);
+}
+
+int ba_trial_host_packed(ba_handle h, const double* in_host, double damping, double pinv_rcond,
+                         const unsigned char* cam_param_mask_host, double* out_host, void* stream) {
+  if (!h || !out_host) return BA_ERR_BAD_ARGUMENT;
+  if (!bound(*h) || !h->sys || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_CUDA(h, cudaSetDevice(h->device));
+  const size_t nR = (size_t)h->n_cam * 9, nt = (size_t)h->n_cam * 3, nx = (size_t)h->n_pt * 3;
+  if (in_host) {
+    if (h->state.cam_t == h->state.cam_R + nR && h->state.pts == h->state.cam_t + nt) {
+      BA_CUDA(h, cudaMemcpyAsync(h->state.cam_R, in_host, (nR + nt + nx) * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      BA_CUDA(h, cudaMemcpyAsync(h->state.cam_R, in_host, nR * sizeof(double), cudaMemcpyHostToDevice, st));
+      BA_CUDA(h, cudaMemcpyAsync(h->state.cam_t, in_host + nR, nt * sizeof(double), cudaMemcpyHostToDevice, st));
+      BA_CUDA(h, cudaMemcpyAsync(h->state.pts, in_host + nR + nt, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+  }
+  int rc = ba_linearize_eliminate(h, damping, pinv_rcond, BA_WANT_SCHUR, stream);
+  if (rc != BA_OK) return rc;
+  if ((rc = ba_solve(h, cam_param_mask_host, stream)) != BA_OK) return rc;
+  if ((rc = ba_backsub_retract_cost(h, stream)) != BA_OK) return rc;
+  BA_CUDA(h, cudaMemcpyAsync(out_host, h->io_out, ((size_t)4 + h->ld + nx) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  return BA_OK;
 }
 
 int ba_scalars_ptr(ba_handle h, double** p) {

@@ -57,7 +57,8 @@ struct Context {
   double* U = nullptr;      // [n_cam][36] HCCs (undamped)       (BA_WANT_BLOCKS)
   double* bC = nullptr;     // [n_cam][6]  bCs                   (BA_WANT_BLOCKS)
   double* W = nullptr;      // [n_obs][18] HCPs, lazily allocated (BA_WANT_BLOCKS)
-  double* dC = nullptr;     // [ld]        reduced solution
+  double* io_out = nullptr; // [4 + ld + 3 n_pt]  {scalars | dC | dP} in one block (one D2H per host-driven trial)
+  double* dC = nullptr;     // [ld]        reduced solution (inside io_out)
   double* Adense = nullptr; // [ld*ld + ld] dense lower-triangular copy + rhs, factored in place
   double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
   unsigned int* solve_flags = nullptr;    // [T*T + 10T] tile / x_k / y_k / Linv row-block ready flags (epoch valued)
@@ -66,7 +67,7 @@ struct Context {
   unsigned int solve_epoch = 0;
   bool solve_attr_set = false;
   bool elim_attr_set[4] = {false, false, false, false};
-  double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero)
+  double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
   double* obs_Jc = nullptr; // [n_obs][12]
   double* obs_Jp = nullptr; // [n_obs][6]

@@ -180,8 +180,17 @@ class DeviceProblem(object):
         self.obs_uv = tt(scene.obs_uv, torch.float64) if scene.n_obs else torch.zeros(2, dtype=torch.float64, device=dev)
         self.cam_slot = tt(scene.cam_slot, torch.int32)
         self.pt_slot = tt(scene.pt_slot, torch.int32)
-        self.params = [dict(R=tt(scene.cam_R, torch.float64), t=tt(scene.cam_t, torch.float64),
-                            x=tt(scene.pts, torch.float64)) for _ in range(2)]
+        # each parameter set is ONE flat allocation [R | t | x] (views below): a host-driven trial
+        # uploads the whole estimate with a single copy (ba_trial_host_packed)
+        nR, nt_, nx = 9 * scene.n_cam, 3 * scene.n_cam, 3 * scene.n_pt
+        host_flat = np.concatenate([np.asarray(scene.cam_R, dtype=np.float64).reshape(-1),
+                                    np.asarray(scene.cam_t, dtype=np.float64).reshape(-1),
+                                    np.asarray(scene.pts, dtype=np.float64).reshape(-1)])
+        self.params = []
+        for _ in range(2):
+            flat = torch.as_tensor(host_flat).to(dev)
+            self.params.append(dict(flat=flat, R=flat[:nR].view(scene.n_cam, 9), t=flat[nR:nR + nt_].view(scene.n_cam, 3),
+                                    x=flat[nR + nt_:].view(scene.n_pt, 3)))
         self.cur = 0
         self.sys_len = int(self.lib.ba_system_size(scene.n_opt_cam))
         self.sys = torch.zeros(max(self.sys_len, 2), dtype=torch.float64, device=dev)
@@ -339,6 +348,26 @@ class DeviceProblem(object):
                                          ptr(out_dP, 3 * sc.n_pt), ctypes.byref(cost), ctypes.byref(cand),
                                          ctypes.byref(status), self._stream()), "ba_trial_host")
         return cost.value, cand.value, status.value
+
+    def trial_host_packed(self, damping, rcond, in_flat, out_flat, cam_param_mask=None):
+        """ba_trial_host_packed: `in_flat` = pinned CPU tensor [R | t | x] (or None), `out_flat` =
+        pinned CPU tensor of 4 + ld + 3 n_pt doubles.  Returns (cost, cand cost, status, dC view,
+        dP view); one H2D, one D2H, one synchronisation."""
+        sc = self.scene
+        n_in = 12 * sc.n_cam + 3 * sc.n_pt
+        n_out = 4 + self.ld + 3 * sc.n_pt
+        mp = None
+        if cam_param_mask is not None:
+            m = np.ascontiguousarray(cam_param_mask, dtype=np.uint8)
+            assert m.shape == (self.n_sys,), 'shape was ' + str(m.shape)
+            self._mask_keepalive = m
+            mp = m.ctypes.data_as(ctypes.c_void_p)
+        self._chk(self.lib.ba_trial_host_packed(self.h, None if in_flat is None else self._host_ptr(in_flat, n_in),
+                                                float(damping), float(rcond), mp, self._host_ptr(out_flat, n_out),
+                                                self._stream()), "ba_trial_host_packed")
+        status = _lib.BA_ERR_ILLCONDITIONED if float(out_flat[2]) != 0.0 else _lib.BA_OK
+        return (float(out_flat[0]), float(out_flat[1]), status, out_flat[4:4 + self.n_sys],
+                out_flat[4 + self.ld:])
 
     def _host_ptr(self, t, count):
         assert (not t.is_cuda) and t.dtype == self.torch.float64 and t.is_contiguous() and t.numel() == count, \

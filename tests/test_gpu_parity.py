@@ -303,3 +303,26 @@ def test_triangulate_all_on_device(cuda_device):
         sel = np.where(ot == j)[0]
         x = triangulate.algebraic_lsq(a["K"], a["Rs"][oc[sel]], a["ts"][oc[sel]], uv[sel])
         assert relerr(b.reconstruction[j], x) < (1e-6 if len(sel) < 3 else 1e-9), (j, len(sel))
+
+
+def test_trial_host_packed_single_copy_each_way(cuda_device):
+    """ba_trial_host_packed: estimate in one pinned buffer [R | t | x], results back in one
+    [scalars | dC | dP] buffer; identical to the staged path."""
+    import torch
+    from pysfm_b200 import synthetic
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+    n_cam, n_pt, k, seed, damping = 17, 900, 5, 22, 1.5
+    b = synthetic.make_scene(n_cam, n_pt, k, seed)
+    ba = BundleAdjuster(b, device=cuda_device, verbose=False)
+    motion, structure = ba.compute_update(damping)
+    cost_ref = ba.compute_cost(b)
+    p = ba._problem
+    sc = p.scene
+    est = np.concatenate([np.asarray(sc.cam_R).reshape(-1), np.asarray(sc.cam_t).reshape(-1), np.asarray(sc.pts).reshape(-1)])
+    in_flat = torch.as_tensor(est, dtype=torch.float64).pin_memory()
+    out_flat = torch.empty(4 + p.ld + 3 * sc.n_pt, dtype=torch.float64).pin_memory()
+    p.upload_state(np.tile(np.eye(3).reshape(1, 9), (sc.n_cam, 1)), np.zeros((sc.n_cam, 3)), np.ones((sc.n_pt, 3)))
+    cost, cand, st, dC, dP = p.trial_host_packed(damping, 1e-5, in_flat, out_flat)
+    assert st == 0 and abs(cost - cost_ref) < 1e-12 * cost_ref and cand < cost
+    assert relerr(-dC.numpy().reshape(-1, 6), motion) < 1e-12
+    assert relerr(-dP.numpy().reshape(-1, 3)[ba._packed.optim_track_indices], structure) < 1e-12
