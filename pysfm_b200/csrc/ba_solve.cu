@@ -51,8 +51,14 @@ __host__ __device__ __forceinline__ size_t packed_block(int a, int b, int nc) {
 __global__ void __launch_bounds__(256)
 expand_system_kernel(const double* __restrict__ packed, int nc, int n_sys, int ld,
                      const unsigned char* __restrict__ mask, bool have_mask,
-                     double* __restrict__ A, double* __restrict__ rhs) {
+                     double* __restrict__ A, double* __restrict__ rhs,
+                     unsigned int* __restrict__ tickets, double* __restrict__ status) {
   const int q = blockIdx.x;  // column
+  if (q == 0 && threadIdx.x == 0) {   // reset the solver's task tickets and status word (saves two memset nodes)
+    tickets[0] = 0u;
+    tickets[1] = 0u;
+    *status = 0.0;
+  }
   const bool free_q = q < n_sys && (!have_mask || mask[q]);
   double* col = A + (size_t)q * ld;
   if (!free_q) {
@@ -153,7 +159,7 @@ struct CholArgs {
   double* __restrict__ rhs;       // [ld] b -> y (forward substitution)
   double* __restrict__ x;         // [ld] solution
   double* __restrict__ LinvT;     // [T][NB*NB]  LinvT[m*NB + c] = (L_jj^{-1})[c][m]
-  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready
+  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready ; [T*T + 10T + 8(iT+j) + b] columns 8b.. of L_ij ready
   unsigned int* __restrict__ tickets; // [0] tile tasks, [1] back-substitution tasks
   double* __restrict__ status;    // set to 1 on a non-positive pivot
   int ld, T;
@@ -207,12 +213,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // (FP64 tensor-core path: mma.sync.m8n8k4.f64, SASS DMMA.8x8x4)
 template <bool NEG>
 __device__ __forceinline__ void tile_dmma(Frag& acc, const double* __restrict__ P,
-                                          const double* __restrict__ Q, int R0, int C0, int lane) {
+                                          const double* __restrict__ Q, int R0, int C0, int lane,
+                                          int m_lo = 0, int m_hi = NB) {
   const int g = lane >> 2, t4 = lane & 3;
   const double* pa = P + t4 * LDT + R0 + g;
   const double* pb = Q + t4 * LDT + C0 + g;
 #pragma unroll 4
-  for (int m0 = 0; m0 < NB; m0 += 4) {
+  for (int m0 = m_lo; m0 < m_hi; m0 += 4) {
     double a[4], b[2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) a[mi] = NEG ? -pa[m0 * LDT + 8 * mi] : pa[m0 * LDT + 8 * mi];
@@ -233,11 +240,12 @@ struct RowTiles {
 };
 
 // W(r, c) -= sum_m P[m*LDT + 8r + .] * P[m*LDT + 8c + .],  c <= r
-__device__ __forceinline__ void diag_rows_dmma(RowTiles& W, const double* __restrict__ P, int r, int lane) {
+__device__ __forceinline__ void diag_rows_dmma(RowTiles& W, const double* __restrict__ P, int r, int lane,
+                                               int m_lo = 0, int m_hi = NB) {
   const int g = lane >> 2, t4 = lane & 3;
   const double* p = P + t4 * LDT + g;
 #pragma unroll 2
-  for (int m0 = 0; m0 < NB; m0 += 4) {
+  for (int m0 = m_lo; m0 < m_hi; m0 += 4) {
     const double* pm = p + m0 * LDT;
     const double a = -pm[8 * r];
 #pragma unroll
@@ -307,6 +315,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   // of column j ends, the next chain task is one block (~1 us) away from starting its own sweep.
   unsigned int* const yflag = g.flags + (size_t)T * T + T;
   unsigned int* const rowflag = g.flags + (size_t)T * T + 2 * T;
+  unsigned int* const colflag = g.flags + (size_t)T * T + 10 * T;   // [(i*T + j)*8 + cb]: columns 8cb.. of L_ij are out
   const int Tm = T - 1;
   for (;;) {
     __syncthreads();
@@ -395,15 +404,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
     // of step k+1 before computing step k put a whole extra tile product behind every late
     // operand -- the last operand of a chain task always is.)
+    // The LAST operand column (k = pj - 1) is consumed column block by column block while its
+    // two tiles are still being produced (their owners publish 8 flags per tile): the fat last
+    // step of a chain task then finishes about one block after the tiles themselves, instead of
+    // a whole two-tile product later.
+    const int kfull = pj > 0 ? pj - 1 : 0;   // steps 0 .. kfull-1 take complete tiles
     int issued = 0;
-    for (int k = 0; k < pj; ++k) {
+    for (int k = 0; k < kfull; ++k) {
       if (issued == k) {
         wait_k(k);
         __syncthreads();
         issue(k);
         issued = k + 1;
       }
-      if (k + 1 < pj) {
+      if (k + 1 < kfull) {
         if (tid == 0) s_task = ready_k(k + 1) ? 1 : 0;
         __syncthreads();
         if (s_task) {
@@ -422,6 +436,68 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
       if (chain) {
         diag_rows_dmma(W, P, r, lane);
+        if (tid < NB) {
+          double s = 0.0;
+#pragma unroll 8
+          for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
+          bacc += s;
+        }
+      }
+      __syncthreads();
+    }
+    if (pj > 0) {
+      const int k = pj - 1;
+      double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
+      double* Q = P + kTileDoubles;
+      const double* gP = g.A + (size_t)(k * NB) * ld + (size_t)pi * NB;
+      const double* gQ = g.A + (size_t)(k * NB) * ld + (size_t)pj * NB;
+      const unsigned int* fP = colflag + ((size_t)pi * T + k) * 8;
+      const unsigned int* fQ = colflag + ((size_t)pj * T + k) * 8;
+      int cb = 0;
+#pragma unroll 1
+      while (cb < 8) {
+        if (tid == 0) {
+          unsigned int f[8], h[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            f[q] = (q >= cb) ? ld_relaxed(fP + q) : epoch;
+            h[q] = (q >= cb) ? ld_relaxed(fQ + q) : epoch;
+          }
+          int e = cb;
+          bool run = true;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q >= cb) {
+              run = run && (f[q] == epoch) && (h[q] == epoch);
+              if (run) e = q + 1;
+            }
+          if (e == cb) e = cb + 1;
+          while (ld_acquire(fP + e - 1) != epoch) __nanosleep(20);
+          while (ld_acquire(fQ + e - 1) != epoch) __nanosleep(20);
+          s_task = e;
+        }
+        __syncthreads();
+        const int ce = s_task;
+        // columns [8cb, 8ce) of both tiles: 64 contiguous doubles each, 32 chunks of 16 B per column
+        for (int ch = tid; ch < 32 * 8 * (ce - cb); ch += kSolveThreads) {
+          const int m = 8 * cb + (ch >> 5), r2 = (ch & 31) * 2;
+          cp_async16(P + m * LDT + r2, gP + (size_t)m * ld + r2);
+          cp_async16(Q + m * LDT + r2, gQ + (size_t)m * ld + r2);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        tile_dmma<true>(acc, P, Q, R0, C0, lane, 8 * cb, 8 * ce);
+        if (chain) diag_rows_dmma(W, P, r, lane, 8 * cb, 8 * ce);
+        cb = ce;
+      }
+      if (chain) {
+        wait_flag(&yflag[k], epoch);
+        __syncthreads();
+        if (tid < NB) {
+          yk[tid] = __ldcg(g.rhs + k * NB + tid);
+        }
+        __syncthreads();
         if (tid < NB) {
           double s = 0.0;
 #pragma unroll 8
@@ -458,7 +534,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // Row blocks are taken in GROUPS [cb, ce): whatever the owner of column pj has already
       // published is processed in one go (one fetch, one pipelined batch of DMMAs), so a task
       // that arrives late catches up at tensor-pipe speed instead of one block per round trip.
-      int cb = 0;
+      int cb = 0, last_cb = 0;
 #pragma unroll 1
       while (cb < 8) {
         if (tid == 0) {
@@ -525,8 +601,18 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           Lout[(size_t)(col + 1) * ld + row] = e1;
         }
         BA_GT(16 + 32 * (t - 52) + 4 * cb + 2, (t == 52 || t == 53) && tid == 0);
+        __syncthreads();   // column blocks cb .. ce-1 of L_{pi,pj} are complete (Ls and global stores issued)
+        if (wid == 0 && ce < 8) {
+          // ... and visible to the tasks that consume this tile column block by column block: warp 0
+          // (the lightest in the update below) pays for the fence -- the barrier ordered
+          // everybody's stores before it -- and the others go on.  The last group is published
+          // together with the tile flag after the loop.
+          __threadfence();
+          __syncwarp();
+          if (lane >= cb && lane < ce) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
+        }
+        last_cb = cb;
         if (chain) {
-          __syncthreads();   // column blocks cb .. ce-1 of L_{j,j-1} are complete in Ls
           const double* q0 = Ls + t4 * LDT + gq;
           for (int m0 = 8 * cb; m0 < 8 * ce; m0 += 4) {
             const double* q = q0 + m0 * LDT;
@@ -546,6 +632,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       if (wid == 7) {
         __threadfence();
         __syncwarp();
+        if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
       }
       BA_TRACE(t, 6);   // panel part done
@@ -863,12 +950,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   const int ld = c.ld, T = ld / NB;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(&c.scalars->status, 0, sizeof(double), st)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(c.solve_tickets, 0, 2 * sizeof(unsigned int), st)) != cudaSuccess) return e;
   // sharded problems: factor the all-reduced copy the peers pushed (ba_comm.cu), not the local contribution
   const double* packed = (c.sys_reduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
   expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask,
-                                           c.Adense, c.Adense + (size_t)ld * ld);
+                                           c.Adense, c.Adense + (size_t)ld * ld, c.solve_tickets, &c.scalars->status);
   c.launches += 1;
   if (!c.solve_attr_set) {
     if ((e = cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
