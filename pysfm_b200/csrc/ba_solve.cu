@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         cp_async_wait<0>();
         __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
         BA_GT(16 + 32 * (t - 52) + 4 * cb + 1, (t == 52 || t == 53) && tid == 0);
+
         // warp w: the 8x8 tiles rows 8w.., column blocks cb .. ce-1.  Tile q contracts over the
         // 8 (q + 1) columns of Linv that are non-zero in its rows: two interleaved accumulator
         // chains, operands of the next step loaded before the DMMAs of this one are issued, no
@@ -606,7 +607,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           // ... and visible to the tasks that consume this tile column block by column block: warp 0
           // (the lightest in the update below) pays for the fence -- the barrier ordered
           // everybody's stores before it -- and the others go on.  The last group is published
-          // together with the tile flag after the loop.
+          // together with the tile flag after the loop.  (Publishing one group LATE, when the
+          // fence is free, measured worse: 0.347 ms against 0.315 ms -- the consumers' lag costs
+          // more than this warp's stall.)
           __threadfence();
           __syncwarp();
           if (lane >= cb && lane < ce) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
@@ -735,7 +738,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           Ld[gq * TS + 4 + t4] = l1;
           BA_CLK0(pb * 4 + 2);
         }
-        __syncthreads();   // (X) Linv_d, Wcol tiles r > pb and Mrow tiles c < pb are in place
+        // (X) Linv_d is in place.  Only the warps that still have work in the sweep take part in
+        // its barriers (named barriers 2 and 3, participant counts known at compile time): a warp
+        // whose row block is finished leaves for the barrier after the loop, so the fence it
+        // issues to publish its rows of the inverse never holds the others up.
+        if (r == 0 || r >= pb) {
+          const int kX = 32 * (pb == 0 ? 8 : 1 + 8 - pb);
+          asm volatile("bar.sync 2, %0;" ::"r"(kX) : "memory");
+        }
         if (r >= pb && r > 0) {
           l0 = Ld[gq * TS + t4];
           l1 = Ld[gq * TS + 4 + t4];
@@ -769,14 +779,22 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           dmma884(c0, c1, Wcol[r * TD + gq * TS + 4 + t4], l1);
           *reinterpret_cast<double2*>(Lp + r * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
         }
-        __syncthreads();   // (Y) Lp, Mp in place; Wcol / Mrow / Ld free again
+        // (Y) Lp, Mp in place; Wcol / Mrow / Ld free again  (warps r >= pb; warp 0 only at pb = 0)
+        if (r >= pb) {
+          const int kY = 32 * (8 - pb);
+          if (kY > 32) asm volatile("bar.sync 3, %0;" ::"r"(kY) : "memory");
+          else __syncwarp();
+        }
         BA_CLK(pb * 4 + 3);
-        if (r == pb) {
+        if (r == pb && pb > 0) {
           // rows 8 pb .. 8 pb + 7 of L_jj^{-1} are final and this warp has nothing left to do in
           // the sweep: make them visible and let the consumers of this column start (the fence
-          // is kept out of the X..Y window, where the whole CTA would wait for it)
+          // is kept out of the X..Y window, where the whole CTA would wait for it).  Row block 0
+          // belongs to warp 0, whose next Gauss-Jordan step is the critical path: warp 1
+          // publishes it together with row block 1.
           __threadfence();
           __syncwarp();
+          if (pb == 1 && lane == 1) st_release(&rowflag[(size_t)j * 8 + 0], epoch);
           if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
           BA_GT(pb, t == 36 && lane == 0);
         }
