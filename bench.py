@@ -353,7 +353,7 @@ def run_ours(args):
         n_pt_local, n_obs_local = sc.n_pt, sc.n_obs
         # Algorithmic bytes per launch of the three kernels of an iteration, their
         # CUDA-event times of this run, and the DRAM traffic ncu measured for one launch of each
-        # (profiles/r1f_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum, --set full capture
+        # (profiles/r1k_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum, --set full capture
         # of this same command at N=1; the reduced system and the factor stay L2-resident, which is
         # why the traffic is BELOW the algorithmic bytes for the first two).
         #   linearize_eliminate: 20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + packed S + rhs + cameras
@@ -362,8 +362,8 @@ def run_ours(args):
         elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * sc.n_cam
         solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (prob.ld * (prob.ld + 1) // 2)
         back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * sc.n_cam
-        ncu_traffic = {"linearize_eliminate_kernel": 17417984, "chol_dataflow_kernel": 6373632,
-                       "backsub_cost_kernel": 16487168} if world == 1 else {}
+        ncu_traffic = {"linearize_eliminate_kernel": 17419264, "chol_dataflow_kernel": 6400768,
+                       "backsub_cost_kernel": 16501504} if world == 1 else {}
         kern = [("linearize_eliminate_kernel", elim_bytes, stage_ms["linearize_eliminate"],
                  "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.75e11 adds/s = 0.172 ms"),
                 ("chol_dataflow_kernel", solve_bytes, stage_ms["solve"],
