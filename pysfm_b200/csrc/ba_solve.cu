@@ -118,6 +118,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
   } while (0)
 __device__ long long g_sweep_clk[64];
 __device__ unsigned long long g_dbg_time[256];
+// trace builds: the producer chain task whose row-block flag times are recorded, and the first of
+// the two consecutive tickets whose group timeline is recorded (set by solve_bench)
+__device__ int g_dbg_producer = 36, g_dbg_consumer = 52;
 #define BA_GT(idx, cond)                                                           \
   do {                                                                             \
     if (cond) {                                                                    \
@@ -561,15 +564,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
         __syncthreads();
         const int ce = s_task;
-        BA_GT(16 + 32 * (t - 52) + 4 * cb + 0, (t == 52 || t == 53) && tid == 0);
+        BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 0, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
 #ifdef BA_SOLVE_TRACE
-        if ((t == 52 || t == 53) && tid == 0) g_dbg_time[80 + 8 * (t - 52) + cb] = ce;
+        if ((t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0) g_dbg_time[80 + 8 * (t - g_dbg_consumer) + cb] = ce;
 #endif
         for (int q = cb; q < ce; ++q) fetch_block(q);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
-        BA_GT(16 + 32 * (t - 52) + 4 * cb + 1, (t == 52 || t == 53) && tid == 0);
+        BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 1, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
 
         // warp w: the 8x8 tiles rows 8w.., column blocks cb .. ce-1.  Tile q contracts over the
         // 8 (q + 1) columns of Linv that are non-zero in its rows: two interleaved accumulator
@@ -601,7 +604,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           Lout[(size_t)col * ld + row] = e0;
           Lout[(size_t)(col + 1) * ld + row] = e1;
         }
-        BA_GT(16 + 32 * (t - 52) + 4 * cb + 2, (t == 52 || t == 53) && tid == 0);
+        BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 2, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
         __syncthreads();   // column blocks cb .. ce-1 of L_{pi,pj} are complete (Ls and global stores issued)
         if (wid == 0 && ce < 8) {
           // ... and visible to the tasks that consume this tile column block by column block: warp 0
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
               if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
           }
         }
-        BA_GT(16 + 32 * (t - 52) + 4 * cb + 3, (t == 52 || t == 53) && tid == 0);
+        BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 3, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
         cb = ce;
       }
       // tile (pi, pj) of L is out.  Only warp 7 pays for the fence (its stores and, through the
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           __syncwarp();
           if (pb == 1 && lane == 1) st_release(&rowflag[(size_t)j * 8 + 0], epoch);
           if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
-          BA_GT(pb, t == 36 && lane == 0);
+          BA_GT(pb, t == g_dbg_producer && lane == 0);
         }
         if (r > pb) {
           const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];

@@ -90,10 +90,10 @@ int main(int argc, char** argv) {
   {
     unsigned long long dt[256];
     CK(cudaMemcpyFromSymbol(dt, ba::g_dbg_time, sizeof dt));
-    printf("row-block flags of C_3 (task 36) released at (us):");
+    printf("row-block flags of chain task C_3 (ticket 36 at T = 19) released at (us):");
     for (int q = 0; q < 8; ++q) printf(" %.2f", (dt[q] - t0) * 1e-3);
     for (int tk = 0; tk < 2; ++tk) {
-      printf("\nconsumer task %d groups: ", tk + 52);
+      printf("\nconsumer ticket %d groups: ", tk + 52);
       for (int q = 0; q < 8; ++q) {
         const unsigned long long* d = dt + 16 + 32 * tk + 4 * q;
         if (!d[0]) continue;
