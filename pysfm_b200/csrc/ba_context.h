@@ -67,6 +67,7 @@ struct Context {
   unsigned int solve_epoch = 0;
   bool solve_attr_set = false;
   bool elim_attr_set[4] = {false, false, false, false};
+  bool backsub_attr_set[3] = {false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
   double* obs_Jc = nullptr; // [n_obs][12]

@@ -363,8 +363,10 @@ __global__ void retract_points_kernel(int n_pt, const int* __restrict__ pt_slot,
 // ------------------------------------------------------------------------------------------
 struct BacksubArgs {
   ObsArgs o;               // o.cam_R/cam_t/pts = CURRENT state (linearisation point)
-  const double* __restrict__ cand_R;
+  const double* __restrict__ cand_R;   // candidate cameras (read; SC = false)
   const double* __restrict__ cand_t;
+  double* cand_R_out;                  // candidate cameras (written by CTA 0; SC = true)
+  double* cand_t_out;
   double* __restrict__ cand_pts;
   const double* __restrict__ dC;    // [6 n_opt_cam]
   const double* __restrict__ Vinv;
@@ -386,8 +388,14 @@ __device__ __forceinline__ double group_sum(double v) {
 // G lanes per point: with tracks of <= 16 (<= 8) observations a warp works on 2 (4) points at a
 // time, which halves (quarters) the number of dependent load -> compute -> reduce round trips
 // each warp goes through; this kernel is bound by that latency chain, not by bytes.
-template <int G>
+// SC = cameras staged in shared memory: every CTA retracts ALL cameras itself at start
+// (R exp(-dC[:3]), t - dC[3:]; a few hundred cameras are cheaper to recompute per CTA than to
+// launch a separate kernel for and gather from L2), keeps the linearisation-point and the
+// candidate cameras in shared memory for its two passes, and CTA 0 writes the candidate cameras
+// out.  SC = false (too many cameras for shared memory): retract_cameras_kernel ran before.
+template <int G, bool SC>
 __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs A) {
+  extern __shared__ __align__(16) double cam_sm[];   // SC: [n_cam][12] state {R, t} | [n_cam][12] candidate
   const ObsArgs& o = A.o;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -395,6 +403,40 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
   constexpr int NG = 32 / G;
   const int sub = lane / G, gl = lane % G;
   double cost_acc = 0.0;
+  if (SC) {
+    for (int i = threadIdx.x; i < o.n_cam; i += blockDim.x) {
+      double R[9], t[3], Rc[9], tc[3];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) R[j] = o.cam_R[9 * i + j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t[j] = o.cam_t[3 * i + j];
+      const int slot = o.cam_slot[i];
+      if (slot >= 0) {
+        double d[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d[j] = -A.dC[6 * slot + j];
+        camera_retract(R, t, d, Rc, tc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Rc[j] = R[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tc[j] = t[j];
+      }
+      double* s0 = cam_sm + 12 * i;
+      double* s1 = cam_sm + 12 * (o.n_cam + i);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) { s0[j] = R[j]; s1[j] = Rc[j]; }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { s0[9 + j] = t[j]; s1[9 + j] = tc[j]; }
+      if (blockIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) A.cand_R_out[9 * i + j] = Rc[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A.cand_t_out[3 * i + j] = tc[j];
+      }
+    }
+    __syncthreads();
+  }
   for (int base = (blockIdx.x * warps_per_cta + wid) * NG; base < o.n_pt; base += gridDim.x * warps_per_cta * NG) {
     const int pt = base + sub;
     const bool live = pt < o.n_pt;
@@ -417,7 +459,8 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
         if (slot < 0) continue;
         const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
         double r[2], Jc[12], Jp[6];
-        observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
+        if (SC) observe(o.intr, o.model, cam_sm + 12 * cam, cam_sm + 12 * cam + 9, x, uv.x, uv.y, r, Jc, Jp);
+        else observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
         const double* d = A.dC + 6 * slot;
         double q0 = 0.0, q1 = 0.0;
 #pragma unroll
@@ -455,7 +498,8 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
         if (o.cam_slot[cam] < 0) continue;
         const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
         double r[2];
-        residual_only(o.intr, o.model, A.cand_R + 9 * cam, A.cand_t + 3 * cam, xc, uv.x, uv.y, r);
+        if (SC) residual_only(o.intr, o.model, cam_sm + 12 * (o.n_cam + cam), cam_sm + 12 * (o.n_cam + cam) + 9, xc, uv.x, uv.y, r);
+        else residual_only(o.intr, o.model, A.cand_R + 9 * cam, A.cand_t + 3 * cam, xc, uv.x, uv.y, r);
         cost_acc += r[0] * r[0] + r[1] * r[1];
       }
     }
@@ -649,7 +693,11 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
 }
 
 cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
-  {
+  // cameras in shared memory (and retracted inside the kernel) while 24 doubles per camera fit
+  // three resident CTAs per SM; otherwise the stand-alone retraction kernel and global gathers
+  const size_t cam_smem = (size_t)c.n_cam * 24 * sizeof(double);
+  const bool sc = cam_smem <= 64 * 1024;
+  if (!sc) {
     const int tb = 128;
     retract_cameras_kernel<<<(c.n_cam + tb - 1) / tb, tb, 0, st>>>(
         c.n_cam, c.cam_slot, c.state.cam_R, c.state.cam_t, c.dC, -1.0, c.cand.cam_R, c.cand.cam_t);
@@ -658,19 +706,33 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   BacksubArgs A;
   A.o = make_obs_args(c, c.state);
   A.cand_R = c.cand.cam_R; A.cand_t = c.cand.cam_t; A.cand_pts = c.cand.pts;
+  A.cand_R_out = c.cand.cam_R; A.cand_t_out = c.cand.cam_t;
   A.dC = c.dC; A.Vinv = c.Vinv; A.bP = c.bP; A.dP = c.dP;
   A.partials = c.partials; A.ticket = c.counters + 1; A.cost_out = &c.scalars->cand_cost;
   // lanes per point: the narrowest group that still holds the longest track in one pass
   const int kmax = c.max_track_len < 1 ? 32 : c.max_track_len;
   // (a software-pipelined single-pass variant at 2 CTAs/SM measured 73 us against 56 us for this
   // one at 3 CTAs/SM: occupancy beats a shorter dependency chain here)
-  if (kmax <= 8) {
-    backsub_cost_kernel<8><<<point_grid(c, 8 * 4, 3), 256, 0, st>>>(A);
-  } else if (kmax <= 16) {
-    backsub_cost_kernel<16><<<point_grid(c, 8 * 2, 3), 256, 0, st>>>(A);
-  } else {
-    backsub_cost_kernel<32><<<point_grid(c, 8, 3), 256, 0, st>>>(A);
-  }
+  const int g = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
+  const int grid = point_grid(c, 8 * (32 / g), 3);
+  cudaError_t e = cudaSuccess;
+#define BA_LAUNCH_BACKSUB(G)                                                                          \
+  do {                                                                                                \
+    if (sc) {                                                                                         \
+      if (!c.backsub_attr_set[G == 8 ? 0 : (G == 16 ? 1 : 2)]) {                                      \
+        e = cudaFuncSetAttribute(backsub_cost_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+        if (e != cudaSuccess) return e;                                                               \
+        c.backsub_attr_set[G == 8 ? 0 : (G == 16 ? 1 : 2)] = true;                                    \
+      }                                                                                               \
+      backsub_cost_kernel<G, true><<<grid, 256, cam_smem, st>>>(A);                                   \
+    } else {                                                                                          \
+      backsub_cost_kernel<G, false><<<grid, 256, 0, st>>>(A);                                         \
+    }                                                                                                 \
+  } while (0)
+  if (g == 8) BA_LAUNCH_BACKSUB(8);
+  else if (g == 16) BA_LAUNCH_BACKSUB(16);
+  else BA_LAUNCH_BACKSUB(32);
+#undef BA_LAUNCH_BACKSUB
   c.launches += 1;
   return cudaGetLastError();
 }
