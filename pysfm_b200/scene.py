@@ -379,12 +379,19 @@ class DeviceProblem(object):
         """Export this rank's comm buffer, exchange the IPC handles with `all_gather(bytes) ->
         [bytes per rank]`, map the peers.  Afterwards `self.sys` views the library-owned buffer."""
         torch = self.torch
+        self._torch_sys = self.sys
         mine = (ctypes.c_ubyte * 64)()
-        self._chk(self.lib.ba_comm_create(self.h, int(rank), int(world), ctypes.cast(mine, ctypes.c_void_p)), "ba_comm_create")
-        handles = all_gather(bytes(mine))
-        assert len(handles) == world and all(len(b) == 64 for b in handles)
-        blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-        self._chk(self.lib.ba_comm_connect(self.h, ctypes.cast(blob, ctypes.c_void_p)), "ba_comm_connect")
+        rc = self.lib.ba_comm_create(self.h, int(rank), int(world), ctypes.cast(mine, ctypes.c_void_p))
+        handles = all_gather(bytes(mine) if rc == _lib.BA_OK else b"")
+        ok = rc == _lib.BA_OK and len(handles) == world and all(len(b) == 64 for b in handles)
+        if ok:
+            blob = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+            ok = self.lib.ba_comm_connect(self.h, ctypes.cast(blob, ctypes.c_void_p)) == _lib.BA_OK
+        # every rank must take the same path: peer memory only if it works everywhere (e.g. not when
+        # CUDA_VISIBLE_DEVICES hides the peers from each process)
+        if not all(all_gather(b"1" if ok else b"0")[r] == b"1" for r in range(world)):
+            self.disable_peer_comm()
+            return False
         sp = ctypes.c_void_p()
         self._chk(self.lib.ba_comm_system_ptr(self.h, ctypes.byref(sp)), "ba_comm_system_ptr")
 
@@ -396,6 +403,14 @@ class DeviceProblem(object):
         self._sys_keepalive = w
         self.sys = torch.as_tensor(w, device=self.device)
         self.peer_comm = True
+        return True
+
+    def disable_peer_comm(self):
+        """Back to the caller-owned (torch) system buffer and host-side collectives."""
+        if getattr(self, "_torch_sys", None) is not None:
+            self.sys = self._torch_sys
+        self._chk(self.lib.ba_bind_system(self.h, _as_vp(self.sys)), "ba_bind_system")
+        self.peer_comm = False
 
     def allreduce_system(self):
         self._chk(self.lib.ba_allreduce_system(self.h, self._stream()), "ba_allreduce_system")
