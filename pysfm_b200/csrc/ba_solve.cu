@@ -394,15 +394,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       wait_flag(&g.flags[(size_t)pj * T + k], epoch);
       if (chain) wait_flag(&yflag[k], epoch);
     };
-    // thread 0: are the operands of step k out already?  (non-blocking; relaxed loads + fence)
-    auto ready_k = [&](int k) -> bool {
-      const unsigned int f0 = ld_relaxed(&g.flags[(size_t)pi * T + k]);
-      const unsigned int f1 = ld_relaxed(&g.flags[(size_t)pj * T + k]);
-      const unsigned int f2 = chain ? ld_relaxed(&yflag[k]) : epoch;
-      const bool ok = f0 == epoch && f1 == epoch && f2 == epoch;
-      if (ok) __threadfence();
-      return ok;
-    };
     // The tiles of step k+1 are prefetched while step k computes ONLY if they are already
     // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
     // of step k+1 before computing step k put a whole extra tile product behind every late
@@ -413,6 +404,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // a whole two-tile product later.
     const int kfull = pj > 0 ? pj - 1 : 0;   // steps 0 .. kfull-1 take complete tiles
     int issued = 0;
+    int ready_upto = -1;   // steps <= ready_upto are known to be published (CTA-uniform)
     for (int k = 0; k < kfull; ++k) {
       if (issued == k) {
         wait_k(k);
@@ -421,9 +413,31 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         issued = k + 1;
       }
       if (k + 1 < kfull) {
-        if (tid == 0) s_task = ready_k(k + 1) ? 1 : 0;
-        __syncthreads();
-        if (s_task) {
+        if (k + 1 > ready_upto) {
+          // (re)scan: warp 0 looks at the next eight steps at once (one lane per step), so that deep
+          // tasks, whose operands are long finished, pay for a scan and a barrier once per eight
+          // steps instead of every step
+          if (wid == 0) {
+            const int kk = k + 1 + lane;
+            bool ok = false;
+            if (lane < 8 && kk < kfull) {
+              const unsigned int f0 = ld_relaxed(&g.flags[(size_t)pi * T + kk]);
+              const unsigned int f1 = ld_relaxed(&g.flags[(size_t)pj * T + kk]);
+              const unsigned int f2 = chain ? ld_relaxed(&yflag[kk]) : epoch;
+              ok = f0 == epoch && f1 == epoch && f2 == epoch;
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, ok) & 0xffu;
+            if (lane == 0) {
+              const unsigned int m = ~mask & 0xffu;
+              const int n = m ? __ffs(m) - 1 : 8;      // consecutive ready steps from k + 1
+              if (n > 0) __threadfence();               // acquire for what the relaxed loads saw
+              s_task = k + n;
+            }
+          }
+          __syncthreads();
+          ready_upto = s_task;
+        }
+        if (k + 1 <= ready_upto) {
           issue(k + 1);
           issued = k + 2;
           cp_async_wait<1>();
