@@ -140,6 +140,7 @@ int ba_destroy(ba_handle h) {
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
     if (h->comm_peer[p] && p != h->comm_rank) cudaIpcCloseMemHandle(h->comm_peer[p]);
+  if (h->rec_scratch) cudaFree(h->rec_scratch);
   if (h->comm_buf) cudaFree(h->comm_buf);
   if (h->comm_done) cudaFree(h->comm_done);
   delete h;
@@ -257,10 +258,6 @@ int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int f
   if ((flags & BA_WANT_BLOCKS) && !h->W) BA_CUDA(h, dev_alloc(&h->W, (size_t)h->n_obs * 18));
   if (flags & BA_WANT_SCHUR) h->sys_reduced = false;   // a fresh local contribution
   cudaError_t e = ba::launch_linearize_eliminate(*h, damping, pinv_rcond, flags, st);
-  if (e == cudaErrorInvalidValue) {
-    h->last_error = "track too long for the shared-memory elimination tile";
-    return BA_ERR_BAD_ARGUMENT;
-  }
   BA_CUDA(h, e);
   return BA_OK;
 }

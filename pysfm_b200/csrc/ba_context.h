@@ -66,7 +66,8 @@ struct Context {
   unsigned long long* solve_trace = nullptr;  // debug timeline (BA_SOLVE_TRACE builds only)
   unsigned int solve_epoch = 0;
   bool solve_attr_set = false;
-  bool elim_attr_set[4] = {false, false, false, false};
+  bool elim_attr_set[8] = {false, false, false, false, false, false, false, false};
+  double* rec_scratch = nullptr;   // [n_obs][56] records of long tracks (elimination kernel, REC_GLOBAL)
   bool backsub_attr_set[3] = {false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)

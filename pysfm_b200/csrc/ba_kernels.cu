@@ -82,6 +82,7 @@ struct ElimArgs {
   double* __restrict__ U;      // [n_cam][36] (blocks)
   double* __restrict__ bC;     // [n_cam][6]  (blocks)
   double* __restrict__ W;      // [n_obs][18] (blocks)
+  double* rec_global;          // [n_obs][56] scratch for the records of long tracks (REC_GLOBAL)
   double* __restrict__ partials;
   unsigned int* __restrict__ ticket;
   double* __restrict__ cost_out;
@@ -118,19 +119,23 @@ __device__ __forceinline__ void bulk_add_block(double* dst, const double* src_sm
                ::"l"(dst), "r"(src) : "memory");
 }
 
-template <bool WANT_BLOCKS, bool WANT_SCHUR>
+// REC_GLOBAL = false: the per-observation records of the point a warp works on live in shared
+// memory (tracks of up to ~430 views fit).  REC_GLOBAL = true (longer tracks somewhere in the
+// scene): they live in a global scratch array indexed by observation, 56 doubles per observation
+// (L2 resident while the point is processed); only the staging slots stay in shared memory.
+template <bool WANT_BLOCKS, bool WANT_SCHUR, bool REC_GLOBAL>
 __global__ void __launch_bounds__(256, 2)
 linearize_eliminate_kernel(const ElimArgs A) {
   extern __shared__ __align__(128) double smem[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  double* const stage = smem + (size_t)wid * elim_warp_doubles(A.kcap);
-  double* const Jcs = stage + kStageDoubles;
-  double* const Wv = Jcs + 12 * A.kcap;
-  double* const Yv = Wv + 18 * A.kcap;
-  double* const jtrs = Yv + 18 * A.kcap;
-  int2* const sbs = reinterpret_cast<int2*>(jtrs + 6 * A.kcap);
+  double* const stage = smem + (size_t)wid * elim_warp_doubles(REC_GLOBAL ? 0 : A.kcap);
+  double* Jcs = stage + kStageDoubles;
+  double* Wv = Jcs + 12 * A.kcap;
+  double* Yv = Wv + 18 * A.kcap;
+  double* jtrs = Yv + 18 * A.kcap;
+  int2* sbs = reinterpret_cast<int2*>(jtrs + 6 * A.kcap);
   double* const my_stage = stage + lane * kStageStride;
   const ObsArgs& o = A.o;
   const double damp1 = 1.0 + A.damping;
@@ -161,6 +166,13 @@ linearize_eliminate_kernel(const ElimArgs A) {
   for (; pt < o.n_pt; pt += stride) {
     const int beg = cur_beg;
     const int k = cur_end - cur_beg;
+    if (REC_GLOBAL) {   // this point's records: [Jc 12k | W 18k | Y 18k | jtr 6k | sb k] at 56 doubles per observation
+      Jcs = A.rec_global + (size_t)beg * 56;
+      Wv = Jcs + 12 * k;
+      Yv = Wv + 18 * k;
+      jtrs = Yv + 18 * k;
+      sbs = reinterpret_cast<int2*>(jtrs + 6 * k);
+    }
     const double x[3] = {pf_x0, pf_x1, pf_x2};
     const bool pt_free = pf_ptslot >= 0;
     const int cam0 = pf_cam;
@@ -670,19 +682,31 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   A.kcap = kcap;
   A.sys = c.sys; A.Vinv = c.Vinv; A.bP = c.bP; A.V = c.V; A.U = c.U; A.bC = c.bC; A.W = c.W;
   A.partials = c.partials; A.ticket = c.counters; A.cost_out = &c.scalars->cost;
-  const size_t per_warp = (size_t)elim_warp_doubles(kcap) * sizeof(double);
   const size_t budget = 200 * 1024;
+  // records in shared memory while at least two warps fit a CTA; otherwise (a track of more than
+  // ~210 views somewhere) in the global scratch array, which is allocated on first use
+  const bool rec_global = (size_t)elim_warp_doubles(kcap) * sizeof(double) * 2 > budget;
+  if (rec_global && !c.rec_scratch) {
+    if ((e = cudaMalloc((void**)&c.rec_scratch, (size_t)(c.n_obs > 0 ? c.n_obs : 1) * 56 * sizeof(double))) != cudaSuccess) return e;
+  }
+  A.rec_global = c.rec_scratch;
+  const size_t per_warp = (size_t)elim_warp_doubles(rec_global ? 0 : kcap) * sizeof(double);
   int warps = (int)(budget / per_warp);
-  if (warps < 1) return cudaErrorInvalidValue;  // track too long for the shared-memory tile
   if (warps > 8) warps = 8;
   const size_t smem = per_warp * warps;
   int ctas_per_sm = (int)((budget + 24 * 1024) / (smem + 1024));
   if (ctas_per_sm > 8 / warps * 4) ctas_per_sm = 8 / warps * 4;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 2) ctas_per_sm = 2;   // __launch_bounds__(256, 2)
   const int grid = point_grid(c, warps, ctas_per_sm);
-  auto kern = blocks ? (schur ? linearize_eliminate_kernel<true, true> : linearize_eliminate_kernel<true, false>)
-                     : (schur ? linearize_eliminate_kernel<false, true> : linearize_eliminate_kernel<false, false>);
-  const int variant = (blocks ? 2 : 0) + (schur ? 1 : 0);
+  typedef void (*ElimKernel)(const ElimArgs);
+  static const ElimKernel table[8] = {
+      linearize_eliminate_kernel<false, false, false>, linearize_eliminate_kernel<false, true, false>,
+      linearize_eliminate_kernel<true, false, false>,  linearize_eliminate_kernel<true, true, false>,
+      linearize_eliminate_kernel<false, false, true>,  linearize_eliminate_kernel<false, true, true>,
+      linearize_eliminate_kernel<true, false, true>,   linearize_eliminate_kernel<true, true, true>};
+  const int variant = (rec_global ? 4 : 0) + (blocks ? 2 : 0) + (schur ? 1 : 0);
+  ElimKernel kern = table[variant];
   if (!c.elim_attr_set[variant]) {   // opt in to the full shared-memory carve-out once
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)) != cudaSuccess) return e;
     c.elim_attr_set[variant] = true;

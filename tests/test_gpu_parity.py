@@ -363,3 +363,34 @@ def test_ragged_tracks_match_oracle(cuda_device):
     ba_oracle.apply_damping(blocks, 5.0)
     S2, b2, _ = ba_oracle.schur(P, blocks)
     assert relerr(S, S2) < 1e-9 and relerr(rhs, b2) < 1e-9
+
+
+def test_very_long_track_uses_global_records(cuda_device):
+    """A track seen by 450 cameras (more than the shared-memory record tile holds): the elimination
+    kernel keeps the per-observation records in its global scratch array instead; results against
+    the CPU oracle."""
+    from oracle import ba_oracle
+    from pysfm_b200 import synthetic
+    from pysfm_b200.bundle import Bundle
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+    n_cam, n_pt = 450, 60
+    a = synthetic.make_arrays(n_cam, n_pt, n_cam, seed=93, noise=0.5)
+    rs = np.random.RandomState(3)
+    keep = np.zeros(len(a["obs_cam"]), bool)
+    for j in range(n_pt):
+        idx = np.where(a["obs_track"] == j)[0]
+        kj = n_cam if j == 0 else rs.randint(20, 60)
+        keep[idx[rs.permutation(len(idx))[:kj]]] = True
+    oc, ot, uv = a["obs_cam"][keep], a["obs_track"][keep], a["obs_uv"][keep]
+    b = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], oc, ot, uv)
+    ba = BundleAdjuster(b, device=cuda_device, verbose=False)
+    P = ba_oracle.Problem(a["K"], a["Rs"], a["ts"], a["pts"], oc, ot, uv, ('gaussian', np.eye(2)),
+                          np.arange(1, n_cam), np.arange(n_pt))
+    motion, structure = ba.compute_update(10.0)
+    m2, s2 = ba_oracle.compute_update(P, 10.0)
+    assert relerr(motion, m2) < 1e-6
+    assert relerr(structure, s2) < 1e-6
+    assert abs(ba.compute_cost(b) - ba_oracle.compute_cost(P)) < 1e-10 * ba_oracle.compute_cost(P)
+    ba.prepare_schur_complement()
+    blocks = ba_oracle.prepare(P)
+    assert relerr(ba.HCCs, blocks['HCCs']) < 1e-9 and relerr(ba.HPPs, blocks['HPPs']) < 1e-9
