@@ -90,6 +90,10 @@ __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Release at gpu scope = fence + store (SASS: MEMBAR.ALL.GPU; ST.STRONG.GPU).  It is cumulative:
+// stores of OTHER threads of the CTA that a barrier (bar.sync, __syncwarp) ordered before it are
+// covered, so no publication below issues a separate __threadfence() first (that second fence
+// cost ~0.4 us on every hop of the chain).
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -488,9 +492,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
               run = run && (f[q] == epoch) && (h[q] == epoch);
               if (run) e = q + 1;
             }
-          if (e == cb) e = cb + 1;
-          while (ld_acquire(fP + e - 1) != epoch) __nanosleep(20);
-          while (ld_acquire(fQ + e - 1) != epoch) __nanosleep(20);
+          if (e == cb) {   // nothing yet: spin on the next block of both (relaxed; the columns are read from L2, see below)
+            e = cb + 1;
+            while (ld_relaxed(fP + cb) != epoch) __nanosleep(20);
+            while (ld_relaxed(fQ + cb) != epoch) __nanosleep(20);
+          }
           s_task = e;
         }
         __syncthreads();
@@ -551,11 +557,29 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // Row blocks are taken in GROUPS [cb, ce): whatever the owner of column pj has already
       // published is processed in one go (one fetch, one pipelined batch of DMMAs), so a task
       // that arrives late catches up at tensor-pipe speed instead of one block per round trip.
-      int cb = 0, last_cb = 0;
+      // Chain tasks fold each finished column block of L_{j,j-1} into the diagonal tile LAZILY:
+      // the next chain task waits for the panel tile, not for W, so while more rows of the
+      // inverse are already there the panel goes first and the update of W (column blocks
+      // [ub, cb)) is caught up on when the task would otherwise spin, or after the loop.
+      auto fold = [&](int b0, int b1) {
+        const double* q0 = Ls + t4 * LDT + gq;
+        for (int m0 = 8 * b0; m0 < 8 * b1; m0 += 4) {
+          const double* q = q0 + m0 * LDT;
+          const double av = -q[8 * r];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
+        }
+      };
+      int cb = 0, last_cb = 0, ub = 0;
 #pragma unroll 1
       while (cb < 8) {
-        if (tid == 0) {
-          // one round trip: all flags at once (relaxed, independent loads) ...
+        // The scan is one round trip: all flags at once, relaxed, independent loads, by a thread
+        // of warp 1 -- warp 0 may still be inside the release that published the previous group.
+        // No acquire follows: the rows are read with cp.async.cg, i.e. from L2, the point of
+        // coherence, after a barrier that follows the flag load; the owner's release made them
+        // visible there before the flag.  (An acquire load costs a second round trip per group.)
+        if (tid == 32) {
           unsigned int f[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
@@ -567,17 +591,25 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
               run = run && (f[q] == epoch);
               if (run) e = q + 1;
             }
-          // ... and a fence as the acquire; only when nothing is ready yet, spin on the next block
+          // only when nothing is ready yet, spin on the next block
           if (e == cb) {
-            e = cb + 1;
-            while (ld_acquire(rf + cb) != epoch) __nanosleep(20);
-          } else {
-            while (ld_acquire(rf + e - 1) != epoch) { }   // already set: one more round trip, no membar
+            if (chain && ub < cb) {
+              e = -1;   // nothing new: use the wait to fold the pending column blocks into W
+            } else {
+              e = cb + 1;
+              while (ld_relaxed(rf + cb) != epoch) __nanosleep(20);
+            }
           }
           s_task = e;
         }
         __syncthreads();
         const int ce = s_task;
+        if (ce < 0) {   // CTA-uniform
+          fold(ub, cb);
+          ub = cb;
+          __syncthreads();   // everybody has read s_task
+          continue;
+        }
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 0, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
 #ifdef BA_SOLVE_TRACE
         if ((t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0) g_dbg_time[80 + 8 * (t - g_dbg_consumer) + cb] = ce;
@@ -627,34 +659,23 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           // together with the tile flag after the loop.  (Publishing one group LATE, when the
           // fence is free, measured worse: 0.347 ms against 0.315 ms -- the consumers' lag costs
           // more than this warp's stall.)
-          __threadfence();
           __syncwarp();
           if (lane >= cb && lane < ce) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         }
         last_cb = cb;
-        if (chain) {
-          const double* q0 = Ls + t4 * LDT + gq;
-          for (int m0 = 8 * cb; m0 < 8 * ce; m0 += 4) {
-            const double* q = q0 + m0 * LDT;
-            const double av = -q[8 * r];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
-          }
-        }
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 3, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
         cb = ce;
       }
-      // tile (pi, pj) of L is out.  Only warp 7 pays for the fence (its stores and, through the
-      // barrier, everybody else's): in a chain task the other warps go straight on to the sweep,
-      // whose first Gauss-Jordan step is longer than the fence.
+      // tile (pi, pj) of L is out.  Only warp 0 pays for the fence (its stores and, through the
+      // barrier, everybody else's): in a chain task it owns the smallest share of the pending
+      // update of W, so the fence hides behind the other warps' DMMAs.
       __syncthreads();
-      if (wid == 7) {
-        __threadfence();
+      if (wid == 0) {
         __syncwarp();
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
       }
+      if (chain && ub < 8) fold(ub, 8);
       BA_TRACE(t, 6);   // panel part done
     }
 
@@ -692,6 +713,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll
       for (int pb = 0; pb < 8; ++pb) {
         double l0 = 0.0, l1 = 0.0;   // Linv_d[gq][t4], Linv_d[gq][t4 + 4]: the DMMA operand layout
+        double mc0[8], mc1[8];       // warp pb: its finished row block of the inverse, tiles c < pb
         if (r == 0) {
           if (pb > 0) asm volatile("bar.sync 1, 64;" ::: "memory");   // D_pb is in Dn
           BA_CLK0(pb * 4 + 0);
@@ -769,26 +791,23 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
         if (r == pb) {
           // finished row block pb of the inverse:  Mp_c = Linv_d M(pb, c), c < pb;  Mp_pb = Linv_d.
-          // It goes to Mp (operand of the update), to LTs (forward substitution) and straight
-          // out to global memory (the tiles above the diagonal of LinvT are zero from allocation
-          // and are never written).
-          Mp[pb * TD + gq * TS + t4] = l0;
-          Mp[pb * TD + gq * TS + 4 + t4] = l1;
-          LTs[(8 * pb + t4) * LDT + 8 * pb + gq] = l0;
-          LTs[(8 * pb + 4 + t4) * LDT + 8 * pb + gq] = l1;
-          LT[(8 * pb + t4) * NB + 8 * pb + gq] = l0;
-          LT[(8 * pb + 4 + t4) * NB + 8 * pb + gq] = l1;
+          // All the products first (independent accumulators: the tensor pipe overlaps them), then
+          // Mp, the operand of the update everybody waits for at (Y); the copies for the forward
+          // substitution and for the consumers of this column are written after (Y).
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             if (c >= pb) break;
-            double c0 = 0.0, c1 = 0.0;
-            dmma884(c0, c1, l0, Mrow[c * TD + t4 * TS + gq]);
-            dmma884(c0, c1, l1, Mrow[c * TD + (4 + t4) * TS + gq]);
-            *reinterpret_cast<double2*>(Mp + c * TD + gq * TS + 2 * t4) = make_double2(c0, c1);
-            LTs[(8 * c + 2 * t4) * LDT + 8 * pb + gq] = c0;
-            LTs[(8 * c + 2 * t4 + 1) * LDT + 8 * pb + gq] = c1;
-            LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = c0;
-            LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = c1;
+            mc0[c] = 0.0; mc1[c] = 0.0;
+            const double b0 = Mrow[c * TD + t4 * TS + gq], b1 = Mrow[c * TD + (4 + t4) * TS + gq];
+            dmma884(mc0[c], mc1[c], l0, b0);
+            dmma884(mc0[c], mc1[c], l1, b1);
+          }
+          Mp[pb * TD + gq * TS + t4] = l0;
+          Mp[pb * TD + gq * TS + 4 + t4] = l1;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c >= pb) break;
+            *reinterpret_cast<double2*>(Mp + c * TD + gq * TS + 2 * t4) = make_double2(mc0[c], mc1[c]);
           }
         } else if (r > pb) {
           double c0 = 0.0, c1 = 0.0;
@@ -803,13 +822,28 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           else __syncwarp();
         }
         BA_CLK(pb * 4 + 3);
+        if (r == pb) {
+          // LTs (forward substitution) and straight out to global memory (the tiles above the
+          // diagonal of LinvT are zero from allocation and are never written)
+          LTs[(8 * pb + t4) * LDT + 8 * pb + gq] = l0;
+          LTs[(8 * pb + 4 + t4) * LDT + 8 * pb + gq] = l1;
+          LT[(8 * pb + t4) * NB + 8 * pb + gq] = l0;
+          LT[(8 * pb + 4 + t4) * NB + 8 * pb + gq] = l1;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c >= pb) break;
+            LTs[(8 * c + 2 * t4) * LDT + 8 * pb + gq] = mc0[c];
+            LTs[(8 * c + 2 * t4 + 1) * LDT + 8 * pb + gq] = mc1[c];
+            LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = mc0[c];
+            LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = mc1[c];
+          }
+        }
         if (r == pb && pb > 0) {
           // rows 8 pb .. 8 pb + 7 of L_jj^{-1} are final and this warp has nothing left to do in
           // the sweep: make them visible and let the consumers of this column start (the fence
           // is kept out of the X..Y window, where the whole CTA would wait for it).  Row block 0
           // belongs to warp 0, whose next Gauss-Jordan step is the critical path: warp 1
           // publishes it together with row block 1.
-          __threadfence();
           __syncwarp();
           if (pb == 1 && lane == 1) st_release(&rowflag[(size_t)j * 8 + 0], epoch);
           if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
@@ -896,7 +930,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll 8
         for (int m = 0; m < mend; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
-        __threadfence();
       }
       __syncthreads();
       if (tid == 0) st_release(&yflag[j], epoch);
@@ -974,7 +1007,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     }
     __syncthreads();
     if (tid < NB) g.x[k * NB + tid] = part[tid] + part[NB + tid] + part[2 * NB + tid] + part[3 * NB + tid];
-    __threadfence();
     __syncthreads();
     if (tid == 0) st_release(&g.flags[(size_t)T * T + k], epoch);
     BA_TRACE(ntasks + bt, 5);
