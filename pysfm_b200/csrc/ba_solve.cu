@@ -97,6 +97,21 @@ __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Column m of a k-major shared tile (64 contiguous doubles at tile + m*LDT) to the global tile
+// (column m at dst + m*ld) as ONE bulk copy on the TMA path, own bulk group; bulk_store_wait()
+// waits for the COMPLETION of the caller's copies (not .read: the bytes are in L2 when it
+// returns).  Every writer of the tile ran fence.proxy.async before the barrier that precedes the
+// call.  Unlike a release (MEMBAR.GPU, which held up the memory traffic of the whole SM for
+// ~0.6 us per publication), the wait is for exactly these bytes and stalls nobody else.
+__device__ __forceinline__ void bulk_store_column(double* dst, int ld, const double* tile, int m) {
+  const unsigned int src = (unsigned int)__cvta_generic_to_shared(tile + m * (NB + 4));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 512;" ::"l"(dst + (size_t)m * ld), "r"(src) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -535,6 +550,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     double* const Cs = buf;                       // [m][row] = C[row][m]      (A operand)
     double* const Bs = buf + kTileDoubles;        // [m][c]   = Linv_pj[c][m]  (B operand), filled block by block
     double* const Ls = buf + 2 * kTileDoubles;    // [m][row] = L_{pi,pj}[row][m]
+    int last_cb = 0;   // first column block of the last group of the panel tile
     if (has_panel) {
       // ---- progressive panel:  L[:, 8cb..8cb+7] = C[:, 0..8cb+7] Linv[8cb..8cb+7, 0..8cb+7]^T ----
 #pragma unroll
@@ -549,11 +565,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       const double* LTp = g.LinvT + (size_t)pj * NB * NB;
       double* Lout = g.A + (size_t)(pj * NB) * ld + (size_t)pi * NB;
       const unsigned int* rf = rowflag + (size_t)pj * 8;
-      // thread tid fetches the 16-byte chunk (m = tid >> 2, columns 8cb + 2 (tid & 3) ..) of a block
-      auto fetch_block = [&](int cb) {
-        if (tid < 4 * (8 * cb + 8))
-          cp_async16(Bs + (tid >> 2) * LDT + 8 * cb + 2 * (tid & 3), LTp + (size_t)(tid >> 2) * NB + 8 * cb + 2 * (tid & 3));
-      };
       // Row blocks are taken in GROUPS [cb, ce): whatever the owner of column pj has already
       // published is processed in one go (one fetch, one pipelined batch of DMMAs), so a task
       // that arrives late catches up at tensor-pipe speed instead of one block per round trip.
@@ -571,42 +582,66 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
         }
       };
-      int cb = 0, last_cb = 0, ub = 0;
+      int cb = 0, ub = 0;
+      int pub_lo = -1, pub_hi = 0;   // column blocks whose bulk copies are in flight, flags not yet set (CTA-uniform)
+      // column blocks [b0, b1) of Ls on their way out: at most one column per thread (issuing a bulk
+      // copy costs ~25 ns and serialises inside a warp, so the issue is spread over the CTA)
+      auto pub_issue = [&](int b0, int b1) {
+        const int i = (lane << 3) | wid;
+        if (i < 8 * (b1 - b0)) bulk_store_column(Lout, ld, Ls, 8 * b0 + i);
+      };
+      auto pub_flags = [&]() {   // after every thread's bulk_store_wait() and a barrier
+        if (pub_lo >= 0) {
+          if (wid == 0 && lane >= pub_lo && lane < pub_hi) st_relaxed(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
+          pub_lo = -1;
+        }
+      };
 #pragma unroll 1
       while (cb < 8) {
-        // The scan is one round trip: all flags at once, relaxed, independent loads, by a thread
-        // of warp 1 -- warp 0 may still be inside the release that published the previous group.
-        // No acquire follows: the rows are read with cp.async.cg, i.e. from L2, the point of
-        // coherence, after a barrier that follows the flag load; the owner's release made them
-        // visible there before the flag.  (An acquire load costs a second round trip per group.)
-        if (tid == 32) {
-          unsigned int f[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+        // Warp 1 scans and fetches (warp 0 may still be inside the release that published the
+        // previous group: the two round trips overlap).  The scan is one round trip: all flags at
+        // once, relaxed, independent loads.  No acquire follows: the rows are read with
+        // cp.async.cg, i.e. from L2, the point of coherence, after the flag load returned; the
+        // owner's release made them visible there before the flag.  (An acquire load costs a
+        // second round trip per group.)
+        if (wid == 1) {
           int e = cb;
-          bool run = true;
+          if (lane == 0) {
+            unsigned int f[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q >= cb) {
-              run = run && (f[q] == epoch);
-              if (run) e = q + 1;
-            }
-          // only when nothing is ready yet, spin on the next block
-          if (e == cb) {
-            if (chain && ub < cb) {
-              e = -1;   // nothing new: use the wait to fold the pending column blocks into W
-            } else {
-              e = cb + 1;
-              while (ld_relaxed(rf + cb) != epoch) __nanosleep(20);
-            }
+            for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+            bool run = true;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q >= cb) {
+                run = run && (f[q] == epoch);
+                if (run) e = q + 1;
+              }
+            // only when nothing is ready yet, spin on the next block
+            if (e == cb) e = -1;   // nothing new: flush the pending publication, fold pending column blocks into W
+            s_task = e;
           }
-          s_task = e;
+          e = __shfl_sync(0xffffffffu, e, 0);
+          // rows 8q .. 8q+7 of Linv are columns 8q .. of Bs, 8 (q + 1) entries deep: 16-byte chunks
+          for (int q = cb; q < e; ++q)
+            for (int ch = lane; ch < 4 * (8 * q + 8); ch += 32)
+              cp_async16(Bs + (ch >> 2) * LDT + 8 * q + 2 * (ch & 3), LTp + (size_t)(ch >> 2) * NB + 8 * q + 2 * (ch & 3));
+          cp_async_commit();
         }
         __syncthreads();
         const int ce = s_task;
         if (ce < 0) {   // CTA-uniform
-          fold(ub, cb);
-          ub = cb;
+          const bool idle = pub_lo < 0 && !(chain && ub < cb);
+          if (pub_lo >= 0) {
+            bulk_store_wait();
+            __syncthreads();
+            pub_flags();
+          }
+          if (chain && ub < cb) {
+            fold(ub, cb);
+            ub = cb;
+          }
+          if (idle) __nanosleep(40);
           __syncthreads();   // everybody has read s_task
           continue;
         }
@@ -614,10 +649,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #ifdef BA_SOLVE_TRACE
         if ((t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0) g_dbg_time[80 + 8 * (t - g_dbg_consumer) + cb] = ce;
 #endif
-        for (int q = cb; q < ce; ++q) fetch_block(q);
-        cp_async_commit();
-        cp_async_wait<0>();
+        if (wid == 1) cp_async_wait<0>();
+        bulk_store_wait();   // the previous group has had a scan and a fetch to land in L2
         __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
+        pub_flags();
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 1, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
 
         // warp w: the 8x8 tiles rows 8w.., column blocks cb .. ce-1.  Tile q contracts over the
@@ -643,35 +678,34 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           dmma884(f0, f1, a1, b1);
           e0 += f0; e1 += f1;
           const int col = 8 * q + 2 * t4, row = 8 * wid + gq;
-          if (chain) {
-            Ls[col * LDT + row] = e0;
-            Ls[(col + 1) * LDT + row] = e1;
+          Ls[col * LDT + row] = e0;
+          Ls[(col + 1) * LDT + row] = e1;
+          if (ce == 8) {   // last group: straight out, published by a release right after the loop
+            Lout[(size_t)col * ld + row] = e0;
+            Lout[(size_t)(col + 1) * ld + row] = e1;
           }
-          Lout[(size_t)col * ld + row] = e0;
-          Lout[(size_t)(col + 1) * ld + row] = e1;
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // Ls is read by the bulk copies below
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 2, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
-        __syncthreads();   // column blocks cb .. ce-1 of L_{pi,pj} are complete (Ls and global stores issued)
-        if (wid == 0 && ce < 8) {
-          // ... and visible to the tasks that consume this tile column block by column block: warp 0
-          // (the lightest in the update below) pays for the fence -- the barrier ordered
-          // everybody's stores before it -- and the others go on.  The last group is published
-          // together with the tile flag after the loop.  (Publishing one group LATE, when the
-          // fence is free, measured worse: 0.347 ms against 0.315 ms -- the consumers' lag costs
-          // more than this warp's stall.)
-          __syncwarp();
-          if (lane >= cb && lane < ce) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
+        __syncthreads();   // column blocks cb .. ce-1 of L_{pi,pj} are complete in Ls
+        if (ce < 8) {
+          // ... and on their way to global memory, for the tasks that consume this tile column block
+          // by column block.  Nobody waits here: the copies are waited for, and the flags set, one
+          // scan and one fetch later, when they have all but landed.  The last group goes out
+          // together with the tile flag after the loop.
+          pub_issue(cb, ce);
+          pub_lo = cb;
+          pub_hi = ce;
         }
         last_cb = cb;
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 3, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
         cb = ce;
       }
-      // tile (pi, pj) of L is out.  Only warp 0 pays for the fence (its stores and, through the
-      // barrier, everybody else's): in a chain task it owns the smallest share of the pending
-      // update of W, so the fence hides behind the other warps' DMMAs.
+      // tile (pi, pj) of L is complete.  The last group was stored directly; warp 1 releases it
+      // (warp 0 starts the sweep of a chain task, warp 7 has the most of W left to fold; the
+      // fence stalls global traffic only, and the rest of a chain task works out of shared memory).
       __syncthreads();
-      if (wid == 0) {
-        __syncwarp();
+      if (wid == 1) {
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
       }
