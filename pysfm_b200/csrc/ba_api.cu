@@ -109,7 +109,7 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->io_out, (size_t)4 + c->ld + (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->Adense, (size_t)c->ld * c->ld + c->ld) == cudaSuccess &&
             dev_alloc(&c->LinvT, T * ba::kSolveTile * ba::kSolveTile) == cudaSuccess &&
-            dev_alloc(&c->solve_flags, 9 * T * T + 10 * T) == cudaSuccess &&
+            dev_alloc(&c->solve_flags, ba::solve_flag_count((int)T)) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&

@@ -10,6 +10,11 @@ namespace ba {
 constexpr int kSolveTile = 64;  // Cholesky tile; the reduced system is padded to a multiple
 constexpr int kMaxPeers = 8;    // GPUs of one node (ba_comm.cu)
 
+// Flags of the dataflow solver (u32, epoch valued): [T*T] tile (i,j) | [T] spare | [T] y_k |
+// pad to a multiple of 4 | [8T] rows 8b.. of Linv_kk | [8T*T] columns 8b.. of L_ij.
+__host__ __device__ inline size_t solve_rowflag_base(int T) { return ((size_t)T * T + 2 * (size_t)T + 3) & ~(size_t)3; }
+inline size_t solve_flag_count(int T) { return solve_rowflag_base(T) + 8 * (size_t)T + 8 * (size_t)T * T; }
+
 // doubles reserved per section of the peer-visible comm buffer (even, so that sections stay
 // 16-byte aligned): [contrib | reduced | costs 2*kMaxPeers | flags 3*kMaxPeers u32]
 __host__ __device__ inline size_t comm_pad(size_t sys_len) { return (sys_len + 2 + 31) & ~(size_t)31; }
@@ -61,7 +66,7 @@ struct Context {
   double* dC = nullptr;     // [ld]        reduced solution (inside io_out)
   double* Adense = nullptr; // [ld*ld + ld] dense lower-triangular copy + rhs, factored in place
   double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
-  unsigned int* solve_flags = nullptr;    // [T*T + 10T] tile / x_k / y_k / Linv row-block ready flags (epoch valued)
+  unsigned int* solve_flags = nullptr;    // [solve_flag_count(T)] tile / y_k / Linv row-block / L column-block ready flags (epoch valued)
   unsigned int* solve_tickets = nullptr;  // [2] task tickets of the dataflow solver
   unsigned long long* solve_trace = nullptr;  // debug timeline (BA_SOLVE_TRACE builds only)
   unsigned int solve_epoch = 0;

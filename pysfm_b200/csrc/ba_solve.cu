@@ -40,6 +40,8 @@ namespace ba {
 constexpr int NB = kSolveTile;     // 64
 constexpr int NBP = NB + 1;        // padded row of the diagonal-tile work arrays
 constexpr int kSolveThreads = 256;
+// A quiet NaN with a payload no arithmetic produces: marks entries of x that are not computed yet.
+constexpr long long kNotYet = 0x7ff8dead0000beefLL;
 
 // ------------------------------------------------------------------------------------------
 // packed block index of (a, b), a <= b < nc:  rows of the upper block triangle back to back
@@ -52,8 +54,10 @@ __global__ void __launch_bounds__(256)
 expand_system_kernel(const double* __restrict__ packed, int nc, int n_sys, int ld,
                      const unsigned char* __restrict__ mask, bool have_mask,
                      double* __restrict__ A, double* __restrict__ rhs,
-                     unsigned int* __restrict__ tickets, double* __restrict__ status) {
+                     unsigned int* __restrict__ tickets, double* __restrict__ status, double* __restrict__ x) {
   const int q = blockIdx.x;  // column
+  // the solution vector starts out as "not there yet": the backward substitution polls the data itself
+  if (threadIdx.x == 0) x[q] = __longlong_as_double(kNotYet);
   if (q == 0 && threadIdx.x == 0) {   // reset the solver's task tickets and status word (saves two memset nodes)
     tickets[0] = 0u;
     tickets[1] = 0u;
@@ -96,6 +100,14 @@ __device__ __forceinline__ unsigned int ld_relaxed(const unsigned int* p) {
 // cost ~0.4 us on every hop of the chain).
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   double* const tvec = vec + 6 * NB;
   double* const yk = vec + 7 * NB;
   __shared__ int s_task;
+  __shared__ __align__(16) unsigned int s_snap[8];   // asynchronous snapshot of the 8 row-block flags a task polls
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
@@ -336,8 +349,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   // tasks) each finished column block is folded into the diagonal tile at once.  When the sweep
   // of column j ends, the next chain task is one block (~1 us) away from starting its own sweep.
   unsigned int* const yflag = g.flags + (size_t)T * T + T;
-  unsigned int* const rowflag = g.flags + (size_t)T * T + 2 * T;
-  unsigned int* const colflag = g.flags + (size_t)T * T + 10 * T;   // [(i*T + j)*8 + cb]: columns 8cb.. of L_ij are out
+  unsigned int* const rowflag = g.flags + solve_rowflag_base(T);          // 8 per diagonal tile, 32-byte aligned
+  unsigned int* const colflag = g.flags + solve_rowflag_base(T) + 8 * T;   // [(i*T + j)*8 + cb]: columns 8cb.. of L_ij are out
   const int Tm = T - 1;
   for (;;) {
     __syncthreads();
@@ -489,47 +502,76 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       const double* gQ = g.A + (size_t)(k * NB) * ld + (size_t)pj * NB;
       const unsigned int* fP = colflag + ((size_t)pi * T + k) * 8;
       const unsigned int* fQ = colflag + ((size_t)pj * T + k) * 8;
-      int cb = 0;
+      // Three cursors (column blocks): P fetched up to pf, acc done up to ca (needs P and Q), and,
+      // in a chain task, W done up to cw (needs P only).  Q of a chain task is the panel tile of the
+      // PREVIOUS chain task, the last thing to arrive; P (a plain panel tile) and y_k are there a
+      // little earlier, so the W half of the step and the y GEMV run while the task would
+      // otherwise wait for Q, and only the acc half is left behind the last block of Q.
+      int ca = 0, pf = 0, cw = chain ? 0 : 8;
+      bool gemv_done = !chain;
 #pragma unroll 1
-      while (cb < 8) {
+      while (ca < 8 || cw < 8) {
         if (tid == 0) {
-          unsigned int f[8], h[8];
+          for (;;) {
+            unsigned int f[8], h[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            f[q] = (q >= cb) ? ld_relaxed(fP + q) : epoch;
-            h[q] = (q >= cb) ? ld_relaxed(fQ + q) : epoch;
-          }
-          int e = cb;
-          bool run = true;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q >= cb) {
-              run = run && (f[q] == epoch) && (h[q] == epoch);
-              if (run) e = q + 1;
+            for (int q = 0; q < 8; ++q) {
+              f[q] = (q >= pf) ? ld_relaxed(fP + q) : epoch;
+              h[q] = (q >= ca) ? ld_relaxed(fQ + q) : epoch;
             }
-          if (e == cb) {   // nothing yet: spin on the next block of both (relaxed; the columns are read from L2, see below)
-            e = cb + 1;
-            while (ld_relaxed(fP + cb) != epoch) __nanosleep(20);
-            while (ld_relaxed(fQ + cb) != epoch) __nanosleep(20);
+            const unsigned int fy = gemv_done ? 0u : ld_relaxed(&yflag[k]);
+            int eP = 0, eQ = 0;
+            bool runP = true, runQ = true;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              runP = runP && (f[q] == epoch);
+              runQ = runQ && (h[q] == epoch);
+              if (runP) eP = q + 1;
+              if (runQ) eQ = q + 1;
+            }
+            const int eA = eP < eQ ? eP : eQ;
+            const bool yr = !gemv_done && fy == epoch && eP == 8;
+            if (eA > ca || eP > cw || yr) {
+              s_task = eP | (eQ << 4) | (yr ? 256 : 0);
+              break;
+            }
+            __nanosleep(20);
           }
-          s_task = e;
         }
         __syncthreads();
-        const int ce = s_task;
-        // columns [8cb, 8ce) of both tiles: 64 contiguous doubles each, 32 chunks of 16 B per column
-        for (int ch = tid; ch < 32 * 8 * (ce - cb); ch += kSolveThreads) {
-          const int m = 8 * cb + (ch >> 5), r2 = (ch & 31) * 2;
+        const int st = s_task;
+        const int eP = st & 15, eQ = (st >> 4) & 15;
+        const bool do_gemv = (st & 256) != 0;
+        const int eA = eP < eQ ? eP : eQ;
+        // columns of the tiles: 64 contiguous doubles each, 32 chunks of 16 B per column
+        for (int ch = tid; ch < 32 * 8 * (eP - pf); ch += kSolveThreads) {
+          const int m = 8 * pf + (ch >> 5), r2 = (ch & 31) * 2;
           cp_async16(P + m * LDT + r2, gP + (size_t)m * ld + r2);
+        }
+        for (int ch = tid; ch < 32 * 8 * (eA - ca); ch += kSolveThreads) {
+          const int m = 8 * ca + (ch >> 5), r2 = (ch & 31) * 2;
           cp_async16(Q + m * LDT + r2, gQ + (size_t)m * ld + r2);
         }
         cp_async_commit();
+        if (do_gemv && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);
         cp_async_wait<0>();
         __syncthreads();
-        tile_dmma<true>(acc, P, Q, R0, C0, lane, 8 * cb, 8 * ce);
-        if (chain) diag_rows_dmma(W, P, r, lane, 8 * cb, 8 * ce);
-        cb = ce;
+        if (eA > ca) tile_dmma<true>(acc, P, Q, R0, C0, lane, 8 * ca, 8 * eA);
+        if (eP > cw) diag_rows_dmma(W, P, r, lane, 8 * cw, 8 * eP);
+        if (do_gemv) {
+          if (tid < NB) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int m = 0; m < NB; ++m) s += P[m * LDT + tid] * yk[m];
+            bacc += s;
+          }
+          gemv_done = true;
+        }
+        pf = eP;
+        if (cw < eP) cw = eP;
+        if (ca < eA) ca = eA;
       }
-      if (chain) {
+      if (!gemv_done) {
         wait_flag(&yflag[k], epoch);
         __syncthreads();
         if (tid < NB) {
@@ -583,6 +625,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
       };
       int cb = 0, ub = 0;
+      bool have_snap = false;   // s_snap holds (or is about to hold) a snapshot newer than the last scan
       int pub_lo = -1, pub_hi = 0;   // column blocks whose bulk copies are in flight, flags not yet set (CTA-uniform)
       // column blocks [b0, b1) of Ls on their way out: at most one column per thread (issuing a bulk
       // copy costs ~25 ns and serialises inside a warp, so the issue is spread over the CTA)
@@ -606,10 +649,21 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         // second round trip per group.)
         if (wid == 1) {
           int e = cb;
+          if (have_snap) cp_async_wait<0>();
           if (lane == 0) {
+            // first the snapshot that cp.async took while the previous group's DMMAs ran (no
+            // round trip); a fresh scan only if it shows nothing new
             unsigned int f[8];
+            bool fresh = !have_snap;
+            if (have_snap) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+              for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? s_snap[q] : epoch;
+              fresh = s_snap[cb] != epoch;
+            }
+            if (fresh) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+            }
             bool run = true;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -631,6 +685,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         __syncthreads();
         const int ce = s_task;
         if (ce < 0) {   // CTA-uniform
+          have_snap = false;
           const bool idle = pub_lo < 0 && !(chain && ub < cb);
           if (pub_lo >= 0) {
             bulk_store_wait();
@@ -653,6 +708,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         bulk_store_wait();   // the previous group has had a scan and a fetch to land in L2
         __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
         pub_flags();
+        if (ce < 8 && !chain) {   // snapshot of the flags for the next scan, taken under the DMMAs below
+          // (panel tasks only: a chain task gains more from the larger groups a fresh scan finds)
+          if (tid == 32) {
+            cp_async16(s_snap, rf);
+            cp_async16(s_snap + 4, rf + 4);
+            cp_async_commit();
+          }
+          have_snap = true;
+        }
         BA_GT(16 + 32 * (t - g_dbg_consumer) + 4 * cb + 1, (t == g_dbg_consumer || t == g_dbg_consumer + 1) && tid == 0);
 
         // warp w: the 8x8 tiles rows 8w.., column blocks cb .. ce-1.  Tile q contracts over the
@@ -990,7 +1054,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
     if (tid == 0) {
-      while (ld_acquire(&g.flags[(size_t)T * T + 2 * T + (size_t)k * 8 + 7]) != epoch) __nanosleep(20);   // L_kk^{-1}
+      while (ld_acquire(&g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7]) != epoch) __nanosleep(20);   // L_kk^{-1}
       while (ld_acquire(&g.flags[(size_t)T * T + T + k]) != epoch) __nanosleep(20);      // y_k
       for (int i = T - 1; i > k; --i)
         while (ld_acquire(&g.flags[(size_t)i * T + k]) != epoch) __nanosleep(20);        // tiles (i, k)
@@ -1015,9 +1079,16 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     };
     if (k < T - 1) fetch_tile(T - 1);
     for (int i = T - 1; i > k; --i) {
-      wait_flag(&g.flags[(size_t)T * T + i], epoch);       // x_i
-      __syncthreads();
-      const double x0 = __ldcg(g.x + i * NB + lane), x1 = __ldcg(g.x + i * NB + 32 + lane);
+      // x_i is its own flag: every warp polls the 64 values until none is the "not yet" pattern
+      // (8-byte stores are single-copy atomic; no fence on the producer, one round trip here,
+      // no CTA barrier)
+      double x0, x1;
+      for (;;) {
+        x0 = ld_relaxed_f64(g.x + i * NB + lane);
+        x1 = ld_relaxed_f64(g.x + i * NB + 32 + lane);
+        const bool ok = __double_as_longlong(x0) != kNotYet && __double_as_longlong(x1) != kNotYet;
+        if (__all_sync(0xffffffffu, ok)) break;
+      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) cs[q] += la[q] * x0 + lb[q] * x1;
       if (i - 1 > k) fetch_tile(i - 1);
@@ -1040,9 +1111,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       part[q * NB + c] = s;
     }
     __syncthreads();
-    if (tid < NB) g.x[k * NB + tid] = part[tid] + part[NB + tid] + part[2 * NB + tid] + part[3 * NB + tid];
-    __syncthreads();
-    if (tid == 0) st_release(&g.flags[(size_t)T * T + k], epoch);
+    if (tid < NB) {
+      double xv = part[tid] + part[NB + tid] + part[2 * NB + tid] + part[3 * NB + tid];
+      if (__double_as_longlong(xv) == kNotYet) xv = __longlong_as_double(0x7ff8000000000000LL);   // (cannot happen: keeps a NaN solve from hanging)
+      st_relaxed_f64(g.x + k * NB + tid, xv);
+    }
     BA_TRACE(ntasks + bt, 5);
   }
 }
@@ -1054,7 +1127,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   // sharded problems: factor the all-reduced copy the peers pushed (ba_comm.cu), not the local contribution
   const double* packed = (c.sys_reduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
   expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask,
-                                           c.Adense, c.Adense + (size_t)ld * ld, c.solve_tickets, &c.scalars->status);
+                                           c.Adense, c.Adense + (size_t)ld * ld, c.solve_tickets, &c.scalars->status, c.dC);
   c.launches += 1;
   if (!c.solve_attr_set) {
     if ((e = cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

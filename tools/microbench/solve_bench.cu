@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&c.sys, sys_len * 8)); CK(cudaMemcpy(c.sys, packed.data(), sys_len * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c.Adense, ((size_t)ld * ld + ld) * 8));
   CK(cudaMalloc(&c.LinvT, (size_t)T * 4096 * 8)); CK(cudaMemset(c.LinvT, 0, (size_t)T * 4096 * 8));
-  CK(cudaMalloc(&c.solve_flags, ((size_t)9 * T * T + 10 * T) * 4)); CK(cudaMemset(c.solve_flags, 0, ((size_t)9 * T * T + 10 * T) * 4));
+  CK(cudaMalloc(&c.solve_flags, ba::solve_flag_count(T) * 4)); CK(cudaMemset(c.solve_flags, 0, ba::solve_flag_count(T) * 4));
   CK(cudaMalloc(&c.solve_tickets, 8));
   CK(cudaMalloc(&c.dC, ld * 8));
   CK(cudaMalloc(&c.cam_mask, ld));
