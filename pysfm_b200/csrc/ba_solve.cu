@@ -273,20 +273,46 @@ struct RowTiles {
   double t[8][2];
 };
 
-// W(r, c) -= sum_m P[m*LDT + 8r + .] * P[m*LDT + 8c + .],  c <= r
-__device__ __forceinline__ void diag_rows_dmma(RowTiles& W, const double* __restrict__ P, int r, int lane,
-                                               int m_lo = 0, int m_hi = NB) {
+// W(R, c) -= sum_m P[m*LDT + 8R + .] * P[m*LDT + 8c + .],  c <= R, over m in [m_lo, m_hi).
+// The row block R is a COMPILE-TIME constant, dispatched once per call (rows_dispatch): with a
+// run-time r the tile loop reads `if (c <= r) dmma`, the compiler predicates it, and a
+// predicated-off DMMA still holds the FP64 tensor pipe for its whole issue slot -- the lower
+// triangle then costs as much as the full square (tools/microbench/tile_bench.cu: 4696 clk per
+// 64-deep update against 4566 for a full 64^3 product; 3199 with this form and the pairing below;
+// a switch INSIDE the loop is worse, 5271: an indirect branch per k step).
+template <int R>
+__device__ __forceinline__ void diag_rows_dmma_t(RowTiles& W, const double* __restrict__ P, int lane, int m_lo, int m_hi) {
   const int g = lane >> 2, t4 = lane & 3;
   const double* p = P + t4 * LDT + g;
 #pragma unroll 2
   for (int m0 = m_lo; m0 < m_hi; m0 += 4) {
     const double* pm = p + m0 * LDT;
-    const double a = -pm[8 * r];
+    double b[R + 1];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c <= r) dmma884(W.t[c][0], W.t[c][1], a, pm[8 * c]);
+    for (int c = 0; c <= R; ++c) b[c] = pm[8 * c];
+    const double a = -b[R];
+#pragma unroll
+    for (int c = 0; c <= R; ++c) dmma884(W.t[c][0], W.t[c][1], a, b[c]);
   }
 }
+__device__ __forceinline__ void diag_rows_dmma(RowTiles& W, const double* __restrict__ P, int r, int lane,
+                                               int m_lo = 0, int m_hi = NB) {
+  switch (r) {
+    case 0: diag_rows_dmma_t<0>(W, P, lane, m_lo, m_hi); break;
+    case 1: diag_rows_dmma_t<1>(W, P, lane, m_lo, m_hi); break;
+    case 2: diag_rows_dmma_t<2>(W, P, lane, m_lo, m_hi); break;
+    case 3: diag_rows_dmma_t<3>(W, P, lane, m_lo, m_hi); break;
+    case 4: diag_rows_dmma_t<4>(W, P, lane, m_lo, m_hi); break;
+    case 5: diag_rows_dmma_t<5>(W, P, lane, m_lo, m_hi); break;
+    case 6: diag_rows_dmma_t<6>(W, P, lane, m_lo, m_hi); break;
+    default: diag_rows_dmma_t<7>(W, P, lane, m_lo, m_hi); break;
+  }
+}
+
+// Row block of the diagonal tile owned by warp w.  Warps w and w + 4 share a scheduler (and its
+// share of the FP64 tensor pipe); the lower triangle gives row block r r + 1 tiles, so pairing
+// (0,7) (1,6) (2,5) (3,4) puts 9 tiles on every scheduler instead of 6 / 8 / 10 / 12.
+__device__ __forceinline__ int row_block_of_warp(int w) { return w < 4 ? w : 11 - w; }
 
 // 1/d for a pivot d > 0: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) and one third-order
 // Newton step (3 dependent DFMA) -> ~2^-60 relative error, without the special-case branches
@@ -382,7 +408,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     BA_TRACE(t, 2);   // task grabbed
 
     // ---- original tiles first: their latency hides behind the k loop --------------------------
-    const int r = wid;   // row block owned in the diagonal tile
+    const int r = row_block_of_warp(wid);   // row block owned in the diagonal tile
     Frag acc;            // panel tile  A_{pi,pj} - sum_k L_{pi,k} L_{pj,k}^T   (warp tile R0, C0)
     RowTiles W;          // diagonal tile A_jj - sum_k L_jk L_jk^T, lower triangle, row-block owned
     acc.zero();
@@ -614,16 +640,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // the next chain task waits for the panel tile, not for W, so while more rows of the
       // inverse are already there the panel goes first and the update of W (column blocks
       // [ub, cb)) is caught up on when the task would otherwise spin, or after the loop.
-      auto fold = [&](int b0, int b1) {
-        const double* q0 = Ls + t4 * LDT + gq;
-        for (int m0 = 8 * b0; m0 < 8 * b1; m0 += 4) {
-          const double* q = q0 + m0 * LDT;
-          const double av = -q[8 * r];
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c <= r) dmma884(W.t[c][0], W.t[c][1], av, q[8 * c]);
-        }
-      };
+      auto fold = [&](int b0, int b1) { diag_rows_dmma(W, Ls, r, lane, 8 * b0, 8 * b1); };
       int cb = 0, ub = 0;
       bool have_snap = false;   // s_snap holds (or is about to hold) a snapshot newer than the last scan
       int pub_lo = -1, pub_hi = 0;   // column blocks whose bulk copies are in flight, flags not yet set (CTA-uniform)
@@ -723,30 +740,70 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         // 8 (q + 1) columns of Linv that are non-zero in its rows: two interleaved accumulator
         // chains, operands of the next step loaded before the DMMAs of this one are issued, no
         // predication anywhere near the tensor instructions.
-#pragma unroll 1
-        for (int q = cb; q < ce; ++q) {
+        // Tiles are taken in PAIRS (q, q + 1) sharing the A operand -- four accumulator chains in
+        // flight per warp (tile_bench: 3529 clk for all 8 blocks against 4398 one tile at a time)
+        // -- and a leftover single tile with two.
+        {
           const double* pa = Cs + t4 * LDT + 8 * wid + gq;
-          const double* pb = Bs + t4 * LDT + 8 * q + gq;
-          double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
-          double a0 = pa[0], a1 = pa[4 * LDT], b0 = pb[0], b1 = pb[4 * LDT];
-          const int kend = 8 * q + 8;
+          const int row = 8 * wid + gq;
+          int q = cb;
 #pragma unroll 1
-          for (int m0 = 8; m0 < kend; m0 += 8) {
-            const double na0 = pa[m0 * LDT], na1 = pa[(m0 + 4) * LDT];
-            const double nb0 = pb[m0 * LDT], nb1 = pb[(m0 + 4) * LDT];
+          for (; q + 1 < ce; q += 2) {
+            const double* pb = Bs + t4 * LDT + 8 * q + gq;
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+            const int kend = 8 * q + 8;
+#pragma unroll 2
+            for (int m0 = 0; m0 < kend; m0 += 8) {
+              const double a0 = pa[m0 * LDT], a1 = pa[(m0 + 4) * LDT];
+              const double b0 = pb[m0 * LDT], b1 = pb[(m0 + 4) * LDT];
+              const double c0 = pb[m0 * LDT + 8], c1 = pb[(m0 + 4) * LDT + 8];
+              dmma884(e0, e1, a0, b0);
+              dmma884(g0, g1, a0, c0);
+              dmma884(f0, f1, a1, b1);
+              dmma884(h0, h1, a1, c1);
+            }
+            {   // the eight further columns of Linv that only tile q + 1 reaches
+              const double a0 = pa[kend * LDT], a1 = pa[(kend + 4) * LDT];
+              const double c0 = pb[kend * LDT + 8], c1 = pb[(kend + 4) * LDT + 8];
+              dmma884(g0, g1, a0, c0);
+              dmma884(h0, h1, a1, c1);
+            }
+            e0 += f0; e1 += f1; g0 += h0; g1 += h1;
+            const int col = 8 * q + 2 * t4;
+            Ls[col * LDT + row] = e0;
+            Ls[(col + 1) * LDT + row] = e1;
+            Ls[(col + 8) * LDT + row] = g0;
+            Ls[(col + 9) * LDT + row] = g1;
+            if (ce == 8) {   // last group: straight out, published by a release right after the loop
+              Lout[(size_t)col * ld + row] = e0;
+              Lout[(size_t)(col + 1) * ld + row] = e1;
+              Lout[(size_t)(col + 8) * ld + row] = g0;
+              Lout[(size_t)(col + 9) * ld + row] = g1;
+            }
+          }
+          if (q < ce) {
+            const double* pb = Bs + t4 * LDT + 8 * q + gq;
+            double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+            double a0 = pa[0], a1 = pa[4 * LDT], b0 = pb[0], b1 = pb[4 * LDT];
+            const int kend = 8 * q + 8;
+#pragma unroll 1
+            for (int m0 = 8; m0 < kend; m0 += 8) {
+              const double na0 = pa[m0 * LDT], na1 = pa[(m0 + 4) * LDT];
+              const double nb0 = pb[m0 * LDT], nb1 = pb[(m0 + 4) * LDT];
+              dmma884(e0, e1, a0, b0);
+              dmma884(f0, f1, a1, b1);
+              a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+            }
             dmma884(e0, e1, a0, b0);
             dmma884(f0, f1, a1, b1);
-            a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
-          }
-          dmma884(e0, e1, a0, b0);
-          dmma884(f0, f1, a1, b1);
-          e0 += f0; e1 += f1;
-          const int col = 8 * q + 2 * t4, row = 8 * wid + gq;
-          Ls[col * LDT + row] = e0;
-          Ls[(col + 1) * LDT + row] = e1;
-          if (ce == 8) {   // last group: straight out, published by a release right after the loop
-            Lout[(size_t)col * ld + row] = e0;
-            Lout[(size_t)(col + 1) * ld + row] = e1;
+            e0 += f0; e1 += f1;
+            const int col = 8 * q + 2 * t4;
+            Ls[col * LDT + row] = e0;
+            Ls[(col + 1) * LDT + row] = e1;
+            if (ce == 8) {
+              Lout[(size_t)col * ld + row] = e0;
+              Lout[(size_t)(col + 1) * ld + row] = e1;
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // Ls is read by the bulk copies below
