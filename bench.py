@@ -362,12 +362,12 @@ def run_ours(args):
         elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * sc.n_cam
         solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (prob.ld * (prob.ld + 1) // 2)
         back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * sc.n_cam
-        ncu_traffic = {"linearize_eliminate_kernel": 17419264, "chol_dataflow_kernel": 6400768,
-                       "backsub_cost_kernel": 16501504} if world == 1 else {}
+        ncu_traffic = {"linearize_eliminate_kernel": 17674752, "chol_dataflow_kernel": 6428416,
+                       "backsub_cost_kernel": 18520064} if world == 1 else {}
         kern = [("linearize_eliminate_kernel", elim_bytes, stage_ms["linearize_eliminate"],
                  "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.75e11 adds/s = 0.172 ms"),
                 ("chol_dataflow_kernel", solve_bytes, stage_ms["solve"],
-                 "dependency chain of the 6nc' pivots (FP64 latency), not bytes or flops"),
+                 "one SM's FP64 rate per tile column (sweep of the diagonal tile + the next chain task's panel phase: ~12.5 us x T columns), not bytes or chip flops"),
                 ("backsub_cost_kernel", back_bytes, stage_ms["backsub_retract_cost"], "HBM latency / occupancy")]
         kernels = []
         for name, nbytes_, ms_, bound in kern:
