@@ -51,7 +51,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&c.scalars, sizeof(ba::Scalars))); CK(cudaMemset(c.scalars, 0, sizeof(ba::Scalars)));
   CK(cudaMalloc(&c.solve_trace, (size_t)(ntasks + T) * 8 * 8)); CK(cudaMemset(c.solve_trace, 0, (size_t)(ntasks + T) * 64));
   cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-  float best = 1e30f, best_exp = 0;
+  float best = 1e30f, best_exp = 0, sum = 0;
   for (int r = 0; r < reps; ++r) {
     CK(cudaEventRecord(e0));
     CK(ba::launch_solve(c, false, 0));
@@ -59,7 +59,9 @@ int main(int argc, char** argv) {
     CK(cudaEventSynchronize(e1));
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (ms < best) best = ms;
+    if (r > 0) sum += ms;
   }
+  const float mean = reps > 1 ? sum / (reps - 1) : best;
   (void)e2; (void)best_exp;
   std::vector<double> x(ld);
   CK(cudaMemcpy(x.data(), c.dC, ld * 8, cudaMemcpyDeviceToHost));
@@ -70,8 +72,8 @@ int main(int argc, char** argv) {
     rmax = std::max(rmax, fabs(s)); bmax = std::max(bmax, fabs(b[i]));
   }
   ba::Scalars sc; CK(cudaMemcpy(&sc, c.scalars, sizeof sc, cudaMemcpyDeviceToHost));
-  printf("nc=%d n=%d T=%d tasks=%d: solve %.3f ms (best of %d), residual %.3e (rel %.3e), status %g, %.2f GFLOP/s\n", nc, n, T,
-         ntasks, best, reps, rmax, rmax / bmax, sc.status, (double)n * n * n / 3 / (best * 1e-3) / 1e9);
+  printf("nc=%d n=%d T=%d tasks=%d: solve %.3f ms (best of %d; mean %.3f), residual %.3e (rel %.3e), status %g, %.2f GFLOP/s\n", nc, n, T,
+         ntasks, best, reps, mean, rmax, rmax / bmax, sc.status, (double)n * n * n / 3 / (best * 1e-3) / 1e9);
   // timeline of the last run
   std::vector<unsigned long long> tr((size_t)(ntasks + T) * 8);
   CK(cudaMemcpy(tr.data(), c.solve_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
