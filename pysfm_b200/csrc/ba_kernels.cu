@@ -407,8 +407,11 @@ __device__ __forceinline__ double group_sum(double v) {
 // out.  SC = false (too many cameras for shared memory): retract_cameras_kernel ran before.
 template <int G, bool SC>
 __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs A) {
-  extern __shared__ __align__(16) double cam_sm[];   // SC: [n_cam][12] state {R, t} | [n_cam][12] candidate
+  // SC: [n_cam][12] state {R, t} | [n_cam][12] candidate | [n_cam][6] dC of the camera (0 if fixed) | [n_cam] slot
+  extern __shared__ __align__(16) double cam_sm[];
   const ObsArgs& o = A.o;
+  const double* const dC_sm = cam_sm + 24 * o.n_cam;
+  int* const slot_sm = reinterpret_cast<int*>(cam_sm + 30 * o.n_cam);
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
@@ -423,12 +426,19 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
 #pragma unroll
       for (int j = 0; j < 3; ++j) t[j] = o.cam_t[3 * i + j];
       const int slot = o.cam_slot[i];
+      slot_sm[i] = slot;
       if (slot >= 0) {
         double d[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) d[j] = -A.dC[6 * slot + j];
+        for (int j = 0; j < 6; ++j) {
+          const double v = A.dC[6 * slot + j];
+          cam_sm[24 * o.n_cam + 6 * i + j] = v;   // dC_sm[6 i + j]
+          d[j] = -v;
+        }
         camera_retract(R, t, d, Rc, tc);
       } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cam_sm[24 * o.n_cam + 6 * i + j] = 0.0;
 #pragma unroll
         for (int j = 0; j < 9; ++j) Rc[j] = R[j];
 #pragma unroll
@@ -463,17 +473,22 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
     double xc[3] = {x[0], x[1], x[2]};
     // sum_j W_j^T dC_j  ==  sum_j Jp_j^T (Jc_j dC_j)
     double acc[3] = {0, 0, 0};
+    // the lane's first observation stays in registers for the candidate pass below (tracks no
+    // longer than the lane group -- the usual case -- then read their records exactly once)
+    int cam_first = -1;
+    double2 uv_first = make_double2(0.0, 0.0);
     if (pslot >= 0) {
       for (int a = gl; a < k; a += G) {
         const int ob = beg + a;
         const int cam = __ldcs(o.obs_cam + (ob));
-        const int slot = o.cam_slot[cam];
+        const int slot = SC ? slot_sm[cam] : o.cam_slot[cam];
         if (slot < 0) continue;
         const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
+        if (a == gl) { cam_first = cam; uv_first = uv; }
         double r[2], Jc[12], Jp[6];
         if (SC) observe(o.intr, o.model, cam_sm + 12 * cam, cam_sm + 12 * cam + 9, x, uv.x, uv.y, r, Jc, Jp);
         else observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
-        const double* d = A.dC + 6 * slot;
+        const double* d = SC ? dC_sm + 6 * cam : A.dC + 6 * slot;
         double q0 = 0.0, q1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 6; ++j) { q0 += Jc[j] * d[j]; q1 += Jc[6 + j] * d[j]; }
@@ -505,10 +520,18 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
     }
     if (pslot >= 0) {
       for (int a = gl; a < k; a += G) {
-        const int ob = beg + a;
-        const int cam = __ldcs(o.obs_cam + (ob));
-        if (o.cam_slot[cam] < 0) continue;
-        const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
+        int cam;
+        double2 uv;
+        if (a == gl) {   // kept from the first pass (cam_first < 0: no observation in an optimised camera)
+          if (cam_first < 0) continue;
+          cam = cam_first;
+          uv = uv_first;
+        } else {
+          const int ob = beg + a;
+          cam = __ldcs(o.obs_cam + (ob));
+          if ((SC ? slot_sm[cam] : o.cam_slot[cam]) < 0) continue;
+          uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + (ob));
+        }
         double r[2];
         if (SC) residual_only(o.intr, o.model, cam_sm + 12 * (o.n_cam + cam), cam_sm + 12 * (o.n_cam + cam) + 9, xc, uv.x, uv.y, r);
         else residual_only(o.intr, o.model, A.cand_R + 9 * cam, A.cand_t + 3 * cam, xc, uv.x, uv.y, r);
@@ -719,7 +742,7 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
 cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   // cameras in shared memory (and retracted inside the kernel) while 24 doubles per camera fit
   // three resident CTAs per SM; otherwise the stand-alone retraction kernel and global gathers
-  const size_t cam_smem = (size_t)c.n_cam * 24 * sizeof(double);
+  const size_t cam_smem = (size_t)c.n_cam * (30 * sizeof(double) + sizeof(int));   // {R,t} state + candidate, dC, slot
   const bool sc = cam_smem <= 64 * 1024;
   if (!sc) {
     const int tb = 128;
