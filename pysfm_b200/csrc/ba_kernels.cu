@@ -756,11 +756,13 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   A.cand_R_out = c.cand.cam_R; A.cand_t_out = c.cand.cam_t;
   A.dC = c.dC; A.Vinv = c.Vinv; A.bP = c.bP; A.dP = c.dP;
   A.partials = c.partials; A.ticket = c.counters + 1; A.cost_out = &c.scalars->cand_cost;
-  // lanes per point: the narrowest group that still holds the longest track in one pass
+  // lanes per point: the narrowest group that holds the longest track in at most two passes
+  // (a group of 8 with two lanes doing a second observation beats a group of 16 with six idle
+  // lanes at 10 observations per point: 46 -> 43 us -- the kernel is bound by loads in flight)
   const int kmax = c.max_track_len < 1 ? 32 : c.max_track_len;
   // (a software-pipelined single-pass variant at 2 CTAs/SM measured 73 us against 56 us for this
   // one at 3 CTAs/SM: occupancy beats a shorter dependency chain here)
-  const int g = kmax <= 8 ? 8 : (kmax <= 16 ? 16 : 32);
+  const int g = kmax <= 12 ? 8 : (kmax <= 24 ? 16 : 32);
   const int grid = point_grid(c, 8 * (32 / g), 3);
   cudaError_t e = cudaSuccess;
 #define BA_LAUNCH_BACKSUB(G)                                                                          \
