@@ -72,6 +72,7 @@ struct Context {
   unsigned int solve_epoch = 0;
   bool solve_attr_set = false;
   bool elim_attr_set[8] = {false, false, false, false, false, false, false, false};
+  bool elim_group_attr_set[2] = {false, false};
   double* rec_scratch = nullptr;   // [n_obs][56] records of long tracks (elimination kernel, REC_GLOBAL)
   bool backsub_attr_set[3] = {false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)

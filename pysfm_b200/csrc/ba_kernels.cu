@@ -15,6 +15,7 @@
 // global traffic besides the 20-byte observation records is the per-point Vinv/bP record and
 // the FP64 reductions into the L2-resident reduced system.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "ba_context.h"
@@ -73,6 +74,7 @@ struct ElimArgs {
   ObsArgs o;
   double damping, rcond;
   int n_opt_cam, kcap;
+  int gcap;                    // eliminate_group_kernel: observations a warp pass can hold (NPG * longest track)
   int probe;                   // timing probes (tools/elim_probe.py): 1 = skip the reductions, 2 = skip phase D
   size_t rhs_off;              // doubles of packed blocks before the right-hand side
   double* __restrict__ sys;    // packed upper 6x6 blocks (row by row), then rhs [6 n_opt_cam]
@@ -329,6 +331,245 @@ linearize_eliminate_kernel(const ElimArgs A) {
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           if (A.probe != 1) bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Elimination with SEVERAL POINTS PER WARP PASS (short tracks, the common case): with one point per
+// warp, 10 of 32 lanes work in the per-observation phases at 10 observations per point, and those
+// phases are bound by FP64 issue.  Here a warp takes NPG consecutive points whose observations
+// fill its lanes (host guarantees NPG * longest track <= 32):
+//   A  lane = observation: residual, Jc, Jp, W = Jc^T Jp, Jc^T r            (registers)
+//   B  V, bP of each point by masked warp sums; damped V^-1 in every lane of the point
+//   C  Y = W V^-1 and the reduced right-hand side, lane-local; W, Y parked in shared memory
+//   D  one lane per camera pair of the group: the n diagonal pairs first (round 0, lane = own
+//      observation, operands still in registers), then the off-diagonal pairs point by point;
+//      each 6x6 block goes out as one 288-byte bulk reduction, as in the kernel above.
+// Same results as linearize_eliminate_kernel<false, true, false> up to summation order.
+__host__ __device__ __forceinline__ int elim_group_warp_doubles(int cap) {
+  return (kStageDoubles + 37 * cap + 1) & ~1;   // stage | W [cap][18] | Y [cap][18] | sb [cap] (int2)
+}
+
+template <int NPG>
+__global__ void __launch_bounds__(192, 2) eliminate_group_kernel(const ElimArgs A) {
+  extern __shared__ __align__(128) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int cap = A.gcap;
+  double* const stage = smem + (size_t)wid * elim_group_warp_doubles(cap);
+  double* const Wv = stage + kStageDoubles;
+  double* const Yv = Wv + 18 * cap;
+  int2* const sbs = reinterpret_cast<int2*>(Yv + 18 * cap);
+  double* const my_stage = stage + lane * kStageStride;
+  const ObsArgs& o = A.o;
+  const double damp1 = 1.0 + A.damping;
+  double* __restrict__ S = A.sys;
+  double* __restrict__ rhs = A.sys + A.rhs_off;
+
+  double cost_acc = 0.0;
+  const int n_groups = (o.n_pt + NPG - 1) / NPG;
+  const int stride = gridDim.x * warps_per_cta;
+  for (int g = blockIdx.x * warps_per_cta + wid; g < n_groups; g += stride) {
+    const int p0 = g * NPG;
+    // observations e[j] .. e[j+1] belong to point p0 + j (points past the end are empty)
+    int e[NPG + 1];
+#pragma unroll
+    for (int j = 0; j <= NPG; ++j) e[j] = __ldcs(o.pt_ptr + (p0 + j < o.n_pt ? p0 + j : o.n_pt));
+    const int n = e[NPG] - e[0];
+    const int ob = e[0] + lane;
+    const bool active = lane < n;
+    int pi = 0;
+#pragma unroll
+    for (int j = 1; j < NPG; ++j) pi += (ob >= e[j]) ? 1 : 0;
+    int pbeg = e[0];
+#pragma unroll
+    for (int j = 1; j < NPG; ++j)
+      if (pi == j) pbeg = e[j];
+    const int pt = p0 + pi;
+
+    // ---- phase A: lane = observation ---------------------------------------------------------
+    double Vl[6] = {0, 0, 0, 0, 0, 0}, bl[3] = {0, 0, 0};
+    double Jc[12], W[18], jtr[6];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Jc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) W[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) jtr[i] = 0.0;
+    int slot = -1, rowbase = 0;
+    if (active) {
+      const int cam = __ldcs(o.obs_cam + ob);
+      const double2 uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob);
+      const double x[3] = {__ldcs(o.pts + 3 * pt), __ldcs(o.pts + 3 * pt + 1), __ldcs(o.pts + 3 * pt + 2)};
+      const bool pt_free = __ldcs(o.pt_slot + pt) >= 0;
+      slot = o.cam_slot[cam];
+      double r[2], Jp[6];
+      observe(o.intr, o.model, o.cam_R + 9 * cam, o.cam_t + 3 * cam, x, uv.x, uv.y, r, Jc, Jp);
+      Vl[0] = Jp[0] * Jp[0] + Jp[3] * Jp[3];
+      Vl[1] = Jp[0] * Jp[1] + Jp[3] * Jp[4];
+      Vl[2] = Jp[0] * Jp[2] + Jp[3] * Jp[5];
+      Vl[3] = Jp[1] * Jp[1] + Jp[4] * Jp[4];
+      Vl[4] = Jp[1] * Jp[2] + Jp[4] * Jp[5];
+      Vl[5] = Jp[2] * Jp[2] + Jp[5] * Jp[5];
+      bl[0] = Jp[0] * r[0] + Jp[3] * r[1];
+      bl[1] = Jp[1] * r[0] + Jp[4] * r[1];
+      bl[2] = Jp[2] * r[0] + Jp[5] * r[1];
+      if (slot >= 0 && pt_free) cost_acc += r[0] * r[0] + r[1] * r[1];
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) W[rr * 3 + m] = Jc[rr] * Jp[m] + Jc[6 + rr] * Jp[3 + m];
+        jtr[rr] = Jc[rr] * r[0] + Jc[6 + rr] * r[1];
+      }
+      // packed row base: block (slot, b) lives at index rowbase + b, b >= slot
+      rowbase = slot >= 0 ? slot * A.n_opt_cam - slot * (slot - 1) / 2 - slot : 0;
+    }
+
+    // ---- phase B: point blocks (masked warp sums, one point at a time) -----------------------
+    double Vs[6] = {0, 0, 0, 0, 0, 0}, bs[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < NPG; ++j) {
+      if (e[j + 1] == e[j]) continue;   // warp-uniform
+      const bool mine = active && pi == j;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double t = warp_sum(mine ? Vl[i] : 0.0);
+        if (mine) Vs[i] = t;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double t = warp_sum(mine ? bl[i] : 0.0);
+        if (mine) bs[i] = t;
+      }
+    }
+    double Vf[9] = {Vs[0], Vs[1], Vs[2], Vs[1], Vs[3], Vs[4], Vs[2], Vs[4], Vs[5]};
+    Vf[0] *= damp1; Vf[4] *= damp1; Vf[8] *= damp1;
+    if (!active) { Vf[0] = Vf[4] = Vf[8] = 1.0; }   // idle lanes stay on the fast path of the inverse
+    double Vi[9];
+    sym3_pinv(Vf, A.rcond, Vi);
+    if (active && ob == pbeg) {   // first lane of its point
+      A.bP[3 * pt] = bs[0]; A.bP[3 * pt + 1] = bs[1]; A.bP[3 * pt + 2] = bs[2];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) A.Vinv[(size_t)pt * 9 + i] = Vi[i];
+    }
+    // points without observations: zero gradient, pinv of the zero block
+#pragma unroll
+    for (int j = 0; j < NPG; ++j) {
+      if (e[j + 1] != e[j] || p0 + j >= o.n_pt) continue;   // warp-uniform
+      if (lane == j) {
+        const double Z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double Zi[9];
+        sym3_pinv(Z, A.rcond, Zi);
+        A.bP[3 * (p0 + j)] = 0.0; A.bP[3 * (p0 + j) + 1] = 0.0; A.bP[3 * (p0 + j) + 2] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A.Vinv[(size_t)(p0 + j) * 9 + i] = Zi[i];
+      }
+    }
+
+    // ---- phase C: Y = W Vinv, reduced right-hand side (lane-local) ----------------------------
+    double Y[18];
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr) {
+      const double w0 = W[rr * 3], w1 = W[rr * 3 + 1], w2 = W[rr * 3 + 2];
+      Y[rr * 3] = w0 * Vi[0] + w1 * Vi[3] + w2 * Vi[6];
+      Y[rr * 3 + 1] = w0 * Vi[1] + w1 * Vi[4] + w2 * Vi[7];
+      Y[rr * 3 + 2] = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
+    }
+    if (active) {
+      if (slot >= 0) {
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr)
+          atomicAdd(rhs + 6 * slot + rr, jtr[rr] - (Y[rr * 3] * bs[0] + Y[rr * 3 + 1] * bs[1] + Y[rr * 3 + 2] * bs[2]));
+      }
+#pragma unroll
+      for (int i = 0; i < 18; i += 2) {
+        *reinterpret_cast<double2*>(Wv + lane * 18 + i) = make_double2(W[i], W[i + 1]);
+        *reinterpret_cast<double2*>(Yv + lane * 18 + i) = make_double2(Y[i], Y[i + 1]);
+      }
+      sbs[lane] = make_int2(slot, rowbase);
+    }
+    __syncwarp();
+
+    // ---- phase D: one lane per camera pair of the group --------------------------------------
+    int cpairs[NPG];
+    int npairs = n;
+#pragma unroll
+    for (int j = 0; j < NPG; ++j) {
+      const int kj = e[j + 1] - e[j];
+      cpairs[j] = kj * (kj - 1) / 2;
+      npairs += cpairs[j];
+    }
+    for (int q0 = 0; q0 < npairs; q0 += 32) {
+      const int q = q0 + lane;
+      // the previous round's (or pass's) reduction must have finished READING this slot
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (q < npairs) {
+        if (q < n) {
+          // round 0 only (n <= 32): the diagonal pair of this lane's own observation,
+          // -Y W^T + damped Jc^T Jc, straight from registers
+          if (slot >= 0) {
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+              const double y0 = Y[rr * 3], y1 = Y[rr * 3 + 1], y2 = Y[rr * 3 + 2];
+              const double j0 = Jc[rr], j1 = Jc[6 + rr];
+              double v[6];
+#pragma unroll
+              for (int cc = 0; cc < 6; ++cc) {
+                const double d = j0 * Jc[cc] + j1 * Jc[6 + cc];
+                v[cc] = -(y0 * W[cc * 3] + y1 * W[cc * 3 + 1] + y2 * W[cc * 3 + 2]) + ((rr == cc) ? d * damp1 : d);
+              }
+#pragma unroll
+              for (int cc = 0; cc < 6; cc += 2)
+                *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_add_block(S + (size_t)(rowbase + slot) * 36, my_stage);
+          }
+        } else {
+          int idx = q - n, j = 0;
+#pragma unroll
+          for (int jj = 0; jj + 1 < NPG; ++jj)
+            if (j == jj && idx >= cpairs[jj]) { idx -= cpairs[jj]; j = jj + 1; }
+          int start = 0, kj = e[1] - e[0];
+#pragma unroll
+          for (int jj = 1; jj < NPG; ++jj)
+            if (j == jj) { start = e[jj] - e[0]; kj = e[jj + 1] - e[jj]; }
+          int a, b;
+          pair_from_index(idx, kj - 1, a, b);
+          b += 1;
+          const int2 sa = sbs[start + a];
+          if (sa.x >= 0) {
+            const int slot_b = sbs[start + b].x;
+            double Wb[18];
+#pragma unroll
+            for (int i = 0; i < 18; i += 2) {
+              const double2 w = *reinterpret_cast<const double2*>(Wv + (start + b) * 18 + i);
+              Wb[i] = w.x; Wb[i + 1] = w.y;
+            }
+            const double* Ya = Yv + (start + a) * 18;
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+              const double y0 = Ya[rr * 3], y1 = Ya[rr * 3 + 1], y2 = Ya[rr * 3 + 2];
+              double v[6];
+#pragma unroll
+              for (int cc = 0; cc < 6; ++cc)
+                v[cc] = -(y0 * Wb[cc * 3] + y1 * Wb[cc * 3 + 1] + y2 * Wb[cc * 3 + 2]);
+#pragma unroll
+              for (int cc = 0; cc < 6; cc += 2)
+                *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
+          }
         }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -705,6 +946,35 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   A.kcap = kcap;
   A.sys = c.sys; A.Vinv = c.Vinv; A.bP = c.bP; A.V = c.V; A.U = c.U; A.bC = c.bC; A.W = c.W;
   A.partials = c.partials; A.ticket = c.counters; A.cost_out = &c.scalars->cost;
+  // Short tracks, Schur path only: several points per warp pass (eliminate_group_kernel).  OFF by
+  // default -- parity-clean over the whole GPU suite, but 0.320 ms against 0.279 ms at config 2:
+  // the kernel is bound by the drain of its reductions, which 12 warps per SM overlap worse than
+  // 16, not by the per-observation phases this variant speeds up.  Opt in with
+  // PYSFM_B200_ELIM_GROUP=1 (experiments only).
+  {
+    static const bool group_on = getenv("PYSFM_B200_ELIM_GROUP") && getenv("PYSFM_B200_ELIM_GROUP")[0] == '1';
+    const int npg = 3 * kcap <= 32 ? 3 : (2 * kcap <= 32 ? 2 : 1);
+    if (schur && !blocks && probe == 0 && npg > 1 && group_on) {
+      A.gcap = (npg * kcap + 1) & ~1;
+      const int gw = 6;   // warps per CTA, 2 CTAs per SM
+      const size_t gsmem = (size_t)elim_group_warp_doubles(A.gcap) * sizeof(double) * gw;
+      typedef void (*GroupKernel)(const ElimArgs);
+      GroupKernel gk = npg == 3 ? eliminate_group_kernel<3> : eliminate_group_kernel<2>;
+      bool& attr = c.elim_group_attr_set[npg - 2];
+      if (!attr) {
+        if ((e = cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024)) != cudaSuccess) return e;
+        attr = true;
+      }
+      const int n_groups = (c.n_pt + npg - 1) / npg;
+      int grid = (n_groups + gw - 1) / gw;
+      if (grid > 2 * c.num_sms) grid = 2 * c.num_sms;
+      if (grid < 1) grid = 1;
+      if (grid > c.partials_cap) grid = c.partials_cap;
+      gk<<<grid, gw * 32, gsmem, st>>>(A);
+      c.launches += 1;
+      return cudaGetLastError();
+    }
+  }
   const size_t budget = 200 * 1024;
   // records in shared memory while at least two warps fit a CTA; otherwise (a track of more than
   // ~210 views somewhere) in the global scratch array, which is allocated on first use
