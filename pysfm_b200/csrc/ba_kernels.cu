@@ -75,7 +75,7 @@ struct ElimArgs {
   double damping, rcond;
   int n_opt_cam, kcap;
   int gcap;                    // eliminate_group_kernel: observations a warp pass can hold (NPG * longest track)
-  int probe;                   // timing probes (tools/elim_probe.py): 1 = skip the reductions, 2 = skip phase D
+  int probe;                   // timing probes (tools/elim_probe.py): 1 = skip the reductions, 2 = skip phase D, 3 = skip the rhs atomics
   size_t rhs_off;              // doubles of packed blocks before the right-hand side
   double* __restrict__ sys;    // packed upper 6x6 blocks (row by row), then rhs [6 n_opt_cam]
   double* __restrict__ Vinv;   // [n_pt][9]
@@ -276,7 +276,7 @@ linearize_eliminate_kernel(const ElimArgs A) {
       const double y2 = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
       Yv[a * 18 + rr * 3] = y0; Yv[a * 18 + rr * 3 + 1] = y1; Yv[a * 18 + rr * 3 + 2] = y2;
       const int slot = sbs[a].x;
-      if (slot >= 0)
+      if (slot >= 0 && A.probe != 3)
         atomicAdd(rhs + 6 * slot + rr, jtrs[a * 6 + rr] - (y0 * bl[0] + y1 * bl[1] + y2 * bl[2]));
     }
     __syncwarp();

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Timing probes for linearize_eliminate at BASELINE config 2: full kernel, without issuing the
-bulk reductions (flag 16), without phase D altogether (flag 32).  Results of the probe runs are
+bulk reductions (flag 16), without phase D altogether (flag 32), without the scalar atomics of the
+reduced right-hand side (flag 48).  Results of the probe runs are
 wrong by construction; this only answers "where does the time go"."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,7 +21,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "cudamalloc":
     mine = (ctypes.c_ubyte * 64)()
     p._chk(p.lib.ba_comm_create(p.h, 0, 2, ctypes.cast(mine, ctypes.c_void_p)), "ba_comm_create")
     print("system buffer rebound to a cudaMalloc allocation")
-for name, extra in (("full", 0), ("no bulk issue", 16), ("no phase D", 32), ("phases A+B(V,bP) only", -2), ("full", 0)):
+for name, extra in (("full", 0), ("no bulk issue", 16), ("no phase D", 32), ("no rhs atomics", 48), ("phases A+B(V,bP) only", -2), ("full", 0)):
     ts = []
     for it in range(8):
         flush.zero_()
