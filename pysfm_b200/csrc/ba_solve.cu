@@ -19,17 +19,24 @@
 //                          substitution.  Work items are 64x64 tiles of the lower triangle in
 //                          column-major order, handed out through an atomic ticket; a tile
 //                          task is LEFT-LOOKING: it accumulates  A_ij - sum_k L_ik L_jk^T  in
-//                          registers, consuming the L tiles of earlier columns as soon as
-//                          their ready-flags go up (acquire/release through L2), and is
-//                          written exactly once.  Diagonal tasks factor their tile in shared
-//                          memory with a Gauss-Jordan sweep that yields L_jj and L_jj^{-1}
-//                          together, so every panel tile below is a plain GEMM with the
-//                          inverse and the forward substitution y_j = L_jj^{-1}(b_j - ...)
-//                          rides along.  When the tile tickets run out the CTAs take the
-//                          backward-substitution tasks x_k = L_kk^{-T}(y_k - sum_i L_ik^T x_i)
-//                          from a second ticket.  Tickets are handed out in dependency order
-//                          and the grid never exceeds the number of co-resident CTAs, so a
-//                          waiting CTA always waits on a task that is already running.
+//                          registers on the FP64 tensor pipe, consuming the L tiles of earlier
+//                          columns as soon as their ready-flags (epoch valued, in L2) go up,
+//                          and is written exactly once.  A chain task owns a diagonal tile and
+//                          the panel tile left of it: it sweeps the diagonal tile by blocked
+//                          Gauss-Jordan in registers / shared memory into L_jj^{-1} (L_jj is
+//                          never formed), published row block by row block, so that every
+//                          panel tile below is a product with the inverse that tracks the
+//                          sweep, and the forward substitution y_j = L_jj^{-1}(b_j - ...) rides
+//                          along.  Tiles are published column block by column block (bulk
+//                          stores, relaxed flags); the only fences left are the releases of
+//                          the sweep and of the last column group of a tile.  When the tile
+//                          tickets run out the CTAs take the backward-substitution tasks
+//                          x_k = L_kk^{-T}(y_k - sum_i L_ik^T x_i) from a second ticket; x_k is
+//                          its own ready-flag (the solution vector starts out as a NaN pattern
+//                          and is polled).  Tickets are handed out in dependency order and the
+//                          grid never exceeds the number of co-resident CTAs, so a waiting CTA
+//                          always waits on a task that is already running.  DESIGN.md 4.2 has
+//                          the measured timeline and what bounds it.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -372,8 +379,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   //                    diagonal tile without a global-memory round trip and a flag hop.
   // Both kinds consume Linv_jj ROW BLOCK BY ROW BLOCK while the chain task that owns column j is
   // still sweeping: rows 8cb .. 8cb+7 of Linv give columns 8cb .. 8cb+7 of L_ij, and (chain
-  // tasks) each finished column block is folded into the diagonal tile at once.  When the sweep
-  // of column j ends, the next chain task is one block (~1 us) away from starting its own sweep.
+  // tasks) each finished column block is folded into the diagonal tile, lazily: when no further
+  // rows are waiting, or after the last one.  When the sweep of column j ends, the next chain
+  // task is a group of blocks (~2-3 us) away from starting its own sweep.
   unsigned int* const yflag = g.flags + (size_t)T * T + T;
   unsigned int* const rowflag = g.flags + solve_rowflag_base(T);          // 8 per diagonal tile, 32-byte aligned
   unsigned int* const colflag = g.flags + solve_rowflag_base(T) + 8 * T;   // [(i*T + j)*8 + cb]: columns 8cb.. of L_ij are out
