@@ -47,6 +47,37 @@ def test_library_is_sm100a_sass():
     assert "sm_100a" in out
 
 
+def test_hot_kernels_use_the_fp64_tensor_pipe_and_the_tma_path():
+    """SASS of the built library: the solver's tile products are DMMA (FP64 tensor pipe), the
+    elimination kernel hands its 6x6 blocks to the bulk-reduction engine (UBLKRED), the solver
+    publishes tiles with bulk copies (UBLKCP) and stages operands with LDGSTS (cp.async)."""
+    import shutil
+    import subprocess
+    from pysfm_b200 import build
+    path = build.build_library()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True).stdout
+    per_kernel = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_kernel[name] = []
+        elif name is not None:
+            per_kernel[name].append(line)
+    def count(kernel_substr, mnemonic):
+        return sum(sum(mnemonic in l for l in body) for k, body in per_kernel.items() if kernel_substr in k)
+    assert count("chol_dataflow_kernel", "DMMA.8x8x4") > 100
+    assert count("chol_dataflow_kernel", "UBLKCP") >= 1
+    assert count("chol_dataflow_kernel", "LDGSTS") >= 4
+    assert count("linearize_eliminate_kernel", "UBLKRED") >= 4
+    # nothing in the product path may fall back to a local-memory stack of any size that matters
+    assert count("chol_dataflow_kernel", "STL") <= 8
+
+
 def test_no_cpu_fallback_without_cuda():
     import torch
     if torch.cuda.is_available():
