@@ -3,6 +3,11 @@
 //   mode 1: scalar REDG in the r1a pattern (lane = column, 6 strided rows)  [dense ld layout]
 //   mode 2: cp.reduce.async.bulk .add.f64, one 288-byte op per block, issued by one lane per block
 //   mode 3: as 2 but two 6x6 blocks per op where (576 B) -- upper bound for bigger ops
+//   modes 5-8 (r1q, questions left by tools/elim_probe.py: the elimination kernel drains its
+//   reductions at 63 % of mode 2's rate): 288-byte bulk reductions with the kernel's own
+//   constraints -- ONE staging slot per lane (wait_group.read 0 before every round) and/or the
+//   kernel's address distribution (10 of the 55 blocks of a point hit one of the 199 DIAGONAL
+//   blocks, 2,500 updates each per iteration).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o red_bench red_bench.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -80,6 +85,39 @@ __global__ void __launch_bounds__(256) k_bulk(double* S, int nblocks, int groups
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// HOT: 10 of the 55 blocks of a group go to diagonal blocks (a, a), as in the elimination kernel;
+// DEPTH: bulk groups a lane may have in flight before it reuses its staging slot (kernel: 0).
+template <bool HOT, int DEPTH>
+__global__ void __launch_bounds__(256) k_bulk_like_kernel(double* S, int ncam, int nblocks, int groups) {
+  extern __shared__ __align__(128) double stage[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double* my = stage + (size_t)wid * 32 * 36;
+  for (int i = lane; i < 32 * 36; i += 32) my[i] = 1.0;
+  __syncwarp();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int g = 0; g < groups; ++g) {
+    for (int b0 = 0; b0 < 55; b0 += 32) {
+      const int b = b0 + lane;
+      if (DEPTH == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (b < 55) {
+        uint32_t blk = hash32(warp * 7919u + g * 104729u + b * 13u) % nblocks;
+        if (HOT && b < 10) {   // diagonal block (a, a) of a random camera: packed index a*ncam - a(a-1)/2
+          const uint32_t a = hash32(warp * 31u + g * 17u + b) % ncam;
+          blk = a * ncam - a * (a - 1) / 2;
+        }
+        double* dst = S + (size_t)blk * 36;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(my + (size_t)lane * 36);
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 288;" ::"l"(dst), "r"(src) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (DEPTH == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main() {
   const int ncam = 199, ld = 1216;
   const int nblocks = ncam * (ncam + 1) / 2;
@@ -95,7 +133,7 @@ int main() {
     const int grid = 148 * ctas_per_sm, warps = grid * 8;
     const int groups = (total_groups + warps - 1) / warps;
     const double nblk_ops = (double)groups * warps * 55;
-    for (int mode = 0; mode < 5; ++mode) {
+    for (int mode = 0; mode < 9; ++mode) {
       float best = 1e30f;
       for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(e0));
@@ -103,6 +141,10 @@ int main() {
         else if (mode == 1) k_scalar_dense<<<grid, 256>>>(D, ncam, ld, groups);
         else if (mode == 2) { CK(cudaFuncSetAttribute(k_bulk<288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 288)); k_bulk<288><<<grid, 256, 8 * 32 * 288>>>(S, nblocks, groups); }
         else if (mode == 3) { CK(cudaFuncSetAttribute(k_bulk<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 576)); k_bulk<576><<<grid, 256, 8 * 32 * 576>>>(S, nblocks / 2, groups); }
+        else if (mode == 5) k_bulk_like_kernel<false, 1><<<grid, 256, 8 * 32 * 288>>>(S, ncam, nblocks, groups);
+        else if (mode == 6) k_bulk_like_kernel<false, 0><<<grid, 256, 8 * 32 * 288>>>(S, ncam, nblocks, groups);
+        else if (mode == 7) k_bulk_like_kernel<true, 1><<<grid, 256, 8 * 32 * 288>>>(S, ncam, nblocks, groups);
+        else if (mode == 8) k_bulk_like_kernel<true, 0><<<grid, 256, 8 * 32 * 288>>>(S, ncam, nblocks, groups);
         else { CK(cudaFuncSetAttribute(k_bulk<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 96)); k_bulk<96><<<grid, 256, 8 * 32 * 96>>>(S, nblocks * 3, groups); }
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
@@ -110,7 +152,9 @@ int main() {
         if (ms < best) best = ms;
       }
       const char* names[] = {"scalar REDG, block-major contiguous", "scalar REDG, r1a dense pattern",
-                             "bulk reduce 288 B", "bulk reduce 576 B", "bulk reduce 96 B"};
+                             "bulk reduce 288 B", "bulk reduce 576 B", "bulk reduce 96 B",
+                             "288 B, uniform blocks, 2 groups in flight", "288 B, uniform blocks, 1 slot (kernel)",
+                             "288 B, hot diagonal blocks, 2 in flight", "288 B, hot diagonal blocks, 1 slot (kernel)"};
       printf("ctas/sm=%d  %-38s  %8.3f ms   %.3g block-equivalents/s  (%.3g f64 adds/s)\n", ctas_per_sm, names[mode], best,
              nblk_ops / (best * 1e-3), nblk_ops * 36 / (best * 1e-3));
     }
