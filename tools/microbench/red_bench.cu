@@ -129,6 +129,10 @@ int main() {
   CK(cudaMemset(D, 0, (size_t)ld * ld * sizeof(double)));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaFuncSetAttribute(k_bulk_like_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 288));
+  CK(cudaFuncSetAttribute(k_bulk_like_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 288));
+  CK(cudaFuncSetAttribute(k_bulk_like_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 288));
+  CK(cudaFuncSetAttribute(k_bulk_like_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 288));
   for (int ctas_per_sm = 1; ctas_per_sm <= 4; ctas_per_sm *= 2) {
     const int grid = 148 * ctas_per_sm, warps = grid * 8;
     const int groups = (total_groups + warps - 1) / warps;
