@@ -118,6 +118,11 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+C4 = dict(n_cam=2000, n_pt=1_000_000, k=10, seed=4)   # BASELINE config 4 (pysfm_b200.synthetic.CONFIGS["C4"])
+FP64_PEAK_TFLOPS = 37.1   # tools/microbench/dmma_bench.cu on this pool's B200 (profiles/r1o_kernels.md): DFMA = DMMA = 64 FMA/clk/SM
+PARITY_TOL = 1e-6         # north_star: residuals / updates within 1e-6 relative of the reference path
+
+
 def scene_arrays(n_ranks):
     from pysfm_b200 import synthetic
     return synthetic.make_arrays(CAMS, PTS_PER_GPU * n_ranks, K_OBS, SEED)
@@ -203,6 +208,166 @@ def workload_config(n):
             "l2": "L2 flushed (256 MiB write) before every timed step"}
 
 
+def ncu_traffic():
+    """DRAM traffic per launch of the hot kernels from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, config 2, N = 1)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return {k: int(v) for k, v in d["kernels"].items()}, d.get("capture")
+    except Exception:
+        return {}, None
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+class Harness(object):
+    """One scene on the ranks of this job: the LM iteration, its timing, its stages."""
+
+    def __init__(self, a, dev, world, rank):
+        import torch
+        from pysfm_b200.bundle import Bundle
+        from pysfm_b200.bundle_adjuster import BundleAdjuster
+        self.torch, self.dev, self.world, self.rank = torch, dev, world, rank
+        bundle = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"])
+        self.ba = BundleAdjuster(device=dev, verbose=False, shard=(world > 1))
+        self.ba.set_bundle(bundle)
+        self.prob = self.ba._problem
+        self.sc = self.prob.scene
+        self.n_obs_total = len(a["obs_cam"])
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def step(self):
+        from pysfm_b200 import _lib
+        p = self.prob
+        p.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
+        if not p.dist_solve:
+            self.ba._allreduce_system()
+        p.solve(None)
+        p.backsub_retract_cost()
+        self.ba._allreduce_costs()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, steps, warmup, clocks_for=None):
+        """W untimed steps, then K steps, each bracketed by CUDA events on the launching stream, L2
+        flushed before every step; returns (ms total = max over ranks, launches, clocks)."""
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        launches0 = self.prob.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        sampler = ClockSampler(clocks_for) if clocks_for is not None else None
+        if sampler:
+            sampler.__enter__()
+        self.barrier()
+        for s in range(steps):
+            self.flush.zero_()
+            ev[s][0].record()
+            self.step()
+            ev[s][1].record()
+        self.barrier()
+        if sampler:
+            sampler.__exit__()
+        launches = self.prob.launch_count() - launches0
+        total_ms = self.max_over_ranks(float(sum(e0.elapsed_time(e1) for e0, e1 in ev)))
+        return total_ms, launches, (sampler.summary() if sampler else None)
+
+    def stages(self, reps):
+        from pysfm_b200 import _lib
+        torch, p = self.torch, self.prob
+        names = ["linearize_eliminate", "allreduce_system", "solve", "backsub_retract_cost"]
+        out = dict((k, 0.0) for k in names)
+        for _ in range(reps):
+            self.flush.zero_()
+            m = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            m[0].record()
+            p.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
+            m[1].record()
+            if not p.dist_solve:
+                self.ba._allreduce_system()
+            m[2].record()
+            p.solve(None)
+            m[3].record()
+            p.backsub_retract_cost()
+            self.ba._allreduce_costs()
+            m[4].record()
+            torch.cuda.synchronize(self.dev)
+            for i, k in enumerate(names):
+                out[k] += m[i].elapsed_time(m[i + 1]) / reps
+        return out
+
+    def results(self):
+        """(cost, cand_cost, status, dC (nc',6), local dP rows) of the last step."""
+        from pysfm_b200 import _lib
+        cost, cand, status = self.prob.read_scalars()
+        dC = self.prob.get_array(_lib.BA_ARR_DC, (self.sc.n_opt_cam, 6))
+        dP = self.prob.get_array(_lib.BA_ARR_DP, (self.sc.n_pt, 3))
+        return cost, cand, status, dC, dP
+
+
+def run_c4(args, dev, world, rank):
+    """BASELINE config 4 -- 2,000 cameras / 1 M points / 10 M observations -- STRONG scaling: the
+    same scene at every N, points sharded over the ranks, checked against the oracle's step
+    (tests/golden/config4_step.npz, oracle/make_golden_large.py)."""
+    from pysfm_b200 import synthetic
+    gpath = os.path.join(ROOT, "tests", "golden", "config4_step.npz")
+    if not os.path.isfile(gpath):
+        return {"skipped": "tests/golden/config4_step.npz is missing"}
+    t0 = time.perf_counter()
+    a = synthetic.make_arrays(C4["n_cam"], C4["n_pt"], C4["k"], C4["seed"])
+    h = Harness(a, dev, world, rank)
+    setup_s = time.perf_counter() - t0
+    steps = max(3, min(args.steps, 20))
+    total_ms, launches, _ = h.timed(steps, 3)
+    stage_ms = h.stages(min(steps, 5))
+    cost, cand, status, dC, dP = h.results()
+    out = None
+    if rank == 0:
+        g = np.load(gpath)
+        stride = int(g["sample_stride"])
+        n_loc = h.sc.n_pt
+        gs = -np.asarray(g["structure_sample"])           # oracle returns the negated update
+        mine = dP[::stride]
+        par = {"cost_rel": abs(cost - float(g["cost0"])) / float(g["cost0"]),
+               "cand_cost_rel": abs(cand - float(g["cand_cost"])) / float(g["cand_cost"]),
+               "dC_rel": rel(dC, -np.asarray(g["motion"])),
+               "dP_rel_rank0_sample": rel(mine, gs[:len(mine)]), "tol": PARITY_TOL,
+               "against": "oracle/ba_oracle.py step on the same scene (tests/golden/config4_step.npz)"}
+        par["ok"] = bool(status == 0 and max(par["cost_rel"], par["cand_cost_rel"], par["dC_rel"], par["dP_rel_rank0_sample"]) <= PARITY_TOL)
+        n = h.prob.n_sys
+        ms = total_ms / steps
+        out = {"workload": "BASELINE config 4: %d cameras / %d points / %d observations, strong scaling over %d rank(s)" % (
+                   C4["n_cam"], C4["n_pt"], h.n_obs_total, world),
+               "scaling": "strong", "value": h.n_obs_total * steps / (total_ms * 1e-3), "unit": "obs/s", "ms_per_step": ms,
+               "steps": steps, "stages_ms": stage_ms, "gpu_launches": int(launches),
+               "reduced_system": "%d x %d" % (n, n),
+               "solve": ("distributed tile Cholesky over peer memory (fused reduce-scatter + factor + all-gather of L, ba_solve.cu DIST)"
+                         if h.prob.dist_solve else "replicated on every rank" if world > 1 else "single GPU"),
+               "solve_fp64_tflops": n ** 3 / 3.0 / (stage_ms["solve"] * 1e-3) / 1e12,
+               "fp64_tflops_peak_per_gpu": FP64_PEAK_TFLOPS,
+               "final": {"cost": cost, "cand_cost": cand, "solve_status": status},
+               "parity": par, "setup_s": setup_s, "oracle_cpu_s_per_step": float(g["seconds"])}
+    h.barrier()
+    del h
+    return out
+
+
 def run_ours(args):
     # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner)
     # is sent to stderr instead, and the line itself is written through the saved descriptor.
@@ -212,8 +377,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pysfm_b200 import _lib
-    from pysfm_b200.bundle import Bundle
-    from pysfm_b200.bundle_adjuster import BundleAdjuster
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,77 +390,28 @@ def run_ours(args):
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     a = scene_arrays(world)
-    bundle = Bundle.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"])
-    ba = BundleAdjuster(device=dev, verbose=False, shard=(world > 1))
-    ba.set_bundle(bundle)
-    prob = ba._problem
-    sc = prob.scene
-    n_obs_total = len(a["obs_cam"])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def step():
-        prob.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
-        ba._allreduce_system()
-        prob.solve(None)
-        prob.backsub_retract_cost()
-        ba._allreduce_costs()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    launches0 = prob.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
-        barrier()
-        for s in range(args.steps):
-            flush.zero_()
-            ev[s][0].record()
-            step()
-            ev[s][1].record()
-        barrier()
-    launches = prob.launch_count() - launches0
-    total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ev))
-    cost, cand_cost, status = prob.read_scalars()
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    H = Harness(a, dev, world, rank)
+    ba, prob, sc = H.ba, H.prob, H.sc
+    n_obs_total = H.n_obs_total
+    barrier = H.barrier
+    warm = max(args.warmup, 3)
+    total_ms, launches, clocks = H.timed(args.steps, warm, clocks_for=local)
+    cost, cand_cost, status, dC_dev, dP_dev = H.results()
     value = n_obs_total * args.steps / (total_ms * 1e-3)
 
     # ---- per-stage device times (same stream, CUDA events), L2 flushed before each step ------
-    stage_names = ["linearize_eliminate", "allreduce_system", "solve", "backsub_retract_cost"]
-    stage_ms = dict((k, 0.0) for k in stage_names)
-    reps = min(args.steps, 20)
-    for _ in range(reps):
-        flush.zero_()
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        marks[0].record()
-        prob.linearize_eliminate(DAMPING, 1e-5, _lib.BA_WANT_SCHUR)
-        marks[1].record()
-        ba._allreduce_system()
-        marks[2].record()
-        prob.solve(None)
-        marks[3].record()
-        prob.backsub_retract_cost()
-        ba._allreduce_costs()
-        marks[4].record()
-        torch.cuda.synchronize(dev)
-        for i, k in enumerate(stage_names):
-            stage_ms[k] += marks[i].elapsed_time(marks[i + 1]) / reps
+    stage_ms = H.stages(min(args.steps, 20))
+    cost, cand_cost, status, dC_dev, dP_dev = H.results()
 
     # ---- end to end from host buffers -------------------------------------------------------
     # The user-facing call is BundleAdjuster.compute_update(damping) on a bundle that lives in host
     # memory (bundle_adjuster.py:176-208): every step copies the current estimate (cameras + points)
     # from pinned host memory to the device, runs the trial, and copies the camera and point
-    # updates and the two costs back.  Single GPU: ONE C-ABI call (ba_trial_host); sharded: the
-    # staged calls with the host-side all-reduces in between.  The visibility structure and the
-    # measurements are uploaded once by set_bundle, as in the reference's set_bundle; the
-    # "e2e_full_scene" figure re-uploads those as well every step.
+    # updates and the two costs back.  Single GPU: ONE C-ABI call (ba_trial_host_packed, the entry a
+    # reference-side binding would call; BundleAdjuster.compute_update itself adds numpy packing on
+    # the host); sharded: the staged calls with the collectives in between.  The visibility
+    # structure and the measurements are uploaded once by set_bundle, as in the reference's
+    # set_bundle; the "e2e_full_scene" figure re-uploads those as well every step.
     pin = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt).pin_memory()
     est = np.concatenate([np.asarray(sc.cam_R, dtype=np.float64).reshape(-1), np.asarray(sc.cam_t, dtype=np.float64).reshape(-1),
                           np.asarray(sc.pts, dtype=np.float64).reshape(-1)])
@@ -334,36 +448,57 @@ def run_ours(args):
         for _ in range(args.steps):
             e2e_step(full_scene)
         barrier()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+        return H.max_over_ranks(time.perf_counter() - t0)
 
     e2e_s = time_e2e(False)
     e2e_full_s = time_e2e(True)
     e2e_val = n_obs_total * args.steps / e2e_s
     # the e2e result must be the same update the device-resident path produced
-    dC_dev = prob.get_array(_lib.BA_ARR_DC, (prob.n_sys,))
     dC_e2e = out_flat[4:4 + prob.n_sys].numpy() if world == 1 else out_dC.numpy()
-    assert np.allclose(dC_e2e, dC_dev, rtol=1e-9, atol=1e-12)
+    assert np.allclose(dC_e2e, dC_dev.reshape(-1), rtol=1e-9, atol=1e-12)
+    n_sys, ld_sys = prob.n_sys, prob.ld
+    n_pt_local, n_obs_local, n_cam = sc.n_pt, sc.n_obs, sc.n_cam
+    pairs = float(np.sum((np.diff(sc.pt_ptr).astype(np.float64)) * (np.diff(sc.pt_ptr) + 1) / 2))
+    H.barrier()
+    del H, ba, prob
 
+    # ---- BASELINE config 4 (strong scaling), every N, unless --no-c4 -----------------------------
+    c4 = None
+    if not args.no_c4:
+        try:
+            c4 = run_c4(args, dev, world, rank)
+        except Exception as exc:   # the headline line must still be printed; the failure is part of it
+            c4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    ok = True
     if rank == 0:
         peak, peak_src = hbm_peak()
-        n = prob.n_sys
-        n_pt_local, n_obs_local = sc.n_pt, sc.n_obs
+        n = n_sys
+        # ---- parity of THIS run against the CPU oracle on the very same scene ------------------------
+        from oracle import ba_oracle
+        P = oracle_problem(a)
+        t0 = time.perf_counter()
+        o_cost = ba_oracle.compute_cost(P)
+        o_motion, o_structure = ba_oracle.compute_update(P, DAMPING)
+        o_cand = ba_oracle.compute_cost(ba_oracle.apply_update(P, o_motion, o_structure))
+        parity = {"cost_rel": abs(cost - o_cost) / o_cost, "cand_cost_rel": abs(cand_cost - o_cand) / o_cand,
+                  "dC_rel": rel(dC_dev, -o_motion), "dP_rel_rank0_shard": rel(dP_dev, -o_structure[:n_pt_local]),
+                  "tol": PARITY_TOL, "oracle_s": time.perf_counter() - t0,
+                  "against": "oracle/ba_oracle.py (numpy restatement pinned to the unmodified reference) on the same scene"}
+        parity["ok"] = bool(status == 0 and max(parity["cost_rel"], parity["cand_cost_rel"], parity["dC_rel"],
+                                                parity["dP_rel_rank0_shard"]) <= PARITY_TOL)
+        ok = parity["ok"] and not (c4 and (c4.get("error") or (c4.get("parity") and not c4["parity"]["ok"])))
         # Algorithmic bytes per launch of the three kernels of an iteration, their
         # CUDA-event times of this run, and the DRAM traffic ncu measured for one launch of each
-        # (profiles/r1k_kernels.md: dram__bytes_read.sum + dram__bytes_write.sum, --set full capture
-        # of this same command at N=1; the reduced system and the factor stay L2-resident, which is
+        # (profiles/ncu_traffic.json; the reduced system and the factor stay L2-resident, which is
         # why the traffic is BELOW the algorithmic bytes for the first two).
         #   linearize_eliminate: 20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + packed S + rhs + cameras
         #   chol_dataflow:       packed system read once + dense factor written once and read once by the substitutions
         #   backsub_cost:        20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24, dP 24, x' 24)
-        elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * sc.n_cam
-        solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (prob.ld * (prob.ld + 1) // 2)
-        back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * sc.n_cam
-        ncu_traffic = {"linearize_eliminate_kernel": 17674752, "chol_dataflow_kernel": 6428416,
-                       "backsub_cost_kernel": 18520064} if world == 1 else {}
+        elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * n_cam
+        solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (ld_sys * (ld_sys + 1) // 2)
+        back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * n_cam
+        traffic, traffic_src = ncu_traffic() if world == 1 else ({}, None)
         kern = [("linearize_eliminate_kernel", elim_bytes, stage_ms["linearize_eliminate"],
                  "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.75e11 adds/s = 0.172 ms"),
                 ("chol_dataflow_kernel", solve_bytes, stage_ms["solve"],
@@ -373,32 +508,35 @@ def run_ours(args):
         for name, nbytes_, ms_, bound in kern:
             ach = nbytes_ / (ms_ * 1e-3) / 1e9
             kernels.append({"kernel": name, "algorithmic_bytes": int(nbytes_), "ms": ms_, "achieved": ach, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": ncu_traffic.get(name), "real_bound": bound})
+                            "frac": ach / peak, "traffic": traffic.get(name), "real_bound": bound})
         dom = max(kernels, key=lambda kk: kk["ms"])
-        iter_bytes = 40 * n_obs_local + 224 * n_pt_local + 16 * n * n + 288 * sc.n_cam
-        pairs = float(np.sum((np.diff(sc.pt_ptr).astype(np.float64)) * (np.diff(sc.pt_ptr) + 1) / 2))
+        iter_bytes = 40 * n_obs_local + 224 * n_pt_local + 16 * n * n + 288 * n_cam
         flops_iter = 300.0 * n_obs_local + 216.0 * pairs + n ** 3 / 3.0
         adds = 36.0 * pairs + 6.0 * n_obs_local
         elim_s = stage_ms["linearize_eliminate"] * 1e-3
+        iter_s = total_ms / args.steps * 1e-3
         line = {
             "metric": "observations/sec per LM iteration", "value": value, "unit": "obs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "steps": args.steps, "warmup": warm, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
-            "clocks": clocks.summary(),
+            "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "obs/s", "h2d_bytes_per_step": int(h2d_state), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "path": ("pinned host estimate (cameras + points) -> H2D -> linearise/eliminate/solve/back-substitute/"
                              "candidate cost -> D2H of dC, dP, costs; " +
-                             ("one ba_trial_host_packed C-ABI call per step (one H2D, one D2H, one synchronisation)" if world == 1 else
-                              "staged C-ABI calls with the NCCL all-reduces in between"))},
+                             ("one ba_trial_host_packed C-ABI call per step (one H2D, one D2H, one synchronisation) -- the entry "
+                              "a reference-side binding calls; BundleAdjuster.compute_update adds host-side numpy packing on top" if world == 1 else
+                              "staged C-ABI calls with the peer-memory collectives in between"))},
             "e2e_full_scene": {"value": n_obs_total * args.steps / e2e_full_s, "unit": "obs/s",
                                "h2d_bytes_per_step": int(h2d_state + h2d_scene), "d2h_bytes_per_step": int(d2h),
                                "ms_per_step": 1e3 * e2e_full_s / args.steps,
                                "path": "as e2e, plus the observation arrays (pt_ptr, obs_cam, obs_uv) re-uploaded every step"},
             "gpu_launches": int(launches),
+            "parity": parity,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes": dom["algorithmic_bytes"], "kernel_ms": dom["ms"],
                          "note": "dominant kernel by time; its real bound: " + dom["real_bound"]},
             "roofline_kernels": kernels,
@@ -406,12 +544,17 @@ def run_ours(args):
                                       "achieved_adds_per_s": adds / elim_s, "peak_adds_per_s": 5.75e11,
                                       "frac": adds / elim_s / 5.75e11,
                                       "peak_source": "tools/microbench/bulk_issue_bench.cu + red_bench.cu on this pool's B200"},
-            "iteration_roofline": {"algorithmic_bytes": int(iter_bytes), "achieved_GBs": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9,
-                                   "frac_of_hbm_peak": iter_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
-                                   "fp64_flops": flops_iter, "fp64_tflops": flops_iter / (total_ms / args.steps * 1e-3) / 1e12},
+            "iteration_roofline": {"algorithmic_bytes": int(iter_bytes), "achieved_GBs": iter_bytes / iter_s / 1e9,
+                                   "frac_of_hbm_peak": iter_bytes / iter_s / 1e9 / peak,
+                                   "fp64_flops": flops_iter, "fp64_tflops": flops_iter / iter_s / 1e12,
+                                   "fp64_tflops_peak": FP64_PEAK_TFLOPS,
+                                   "fp64_peak_source": "tools/microbench/dmma_bench.cu on this pool's B200 (DFMA = DMMA = 64 FMA/clk/SM; MEASURED_PEAKS.json has no FP64 figure)",
+                                   "frac_of_fp64_peak": flops_iter / iter_s / 1e12 / FP64_PEAK_TFLOPS},
             "stages_ms": stage_ms,
             "final": {"cost": cost, "cand_cost": cand_cost, "solve_status": status},
         }
+        if c4 is not None:
+            line["c4"] = c4
         if world == 1:
             val, ms, cores, sample = time_oracle(a, steps=2, warmup=1, budget_s=25.0)
             line["cpu_baseline"] = {"value": val, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample,
@@ -421,6 +564,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench.py: parity against the oracle failed (see the `parity` blocks of the line)")
 
 
 def main():
@@ -429,6 +574,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-c4", action="store_true", help="skip the BASELINE config 4 (strong scaling) section of the line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

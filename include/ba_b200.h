@@ -55,7 +55,24 @@ enum {
   BA_ERR_CUDA = 2,
   BA_ERR_NCCL = 3,           /* reserved: collectives are issued by the host side */
   BA_ERR_BAD_ARGUMENT = 4,
-  BA_ERR_NOT_BOUND = 5
+  BA_ERR_NOT_BOUND = 5,
+  BA_ERR_NONFINITE = 6,      /* solve_status of ba_read_scalars: a cost came out NaN/Inf (the
+                                reference's drivers run under numpy.seterr(all='raise'),
+                                window_slam.py:70) */
+  BA_ERR_TIMEOUT = 7         /* solve_status: a spin-wait of the solver or of a peer barrier ran
+                                past BA_OPT_SPIN_TIMEOUT_MS (a peer died or a kernel faulted) */
+};
+
+/* options for ba_set_option */
+enum {
+  BA_OPT_SPIN_TIMEOUT_MS = 0,      /* waiting budget of one solver / collective launch (default 10000) */
+  BA_OPT_STRICT_FLAGS = 1,         /* 1: the single-GPU solver publishes its column-block flags with
+                                      release/acquire instead of relaxed stores (default 0) */
+  BA_OPT_DIST_SOLVE_MIN_TILES = 2, /* sharded handles: ba_solve runs the distributed solve when the
+                                      reduced system has at least this many 64-wide tile rows
+                                      (default 32, i.e. >= 2048 camera parameters; 0 = never) */
+  BA_OPT_DIST_BAND = 3,            /* distributed solve: tiles with i - j <= band stay on rank 0 */
+  BA_OPT_SOLVE_GRID_CAP = 4        /* at most this many solver CTAs (0 = one per SM) */
 };
 
 enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */
@@ -108,6 +125,16 @@ int ba_bind_state(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts
 int ba_bind_candidate(ba_handle h, double* cam_R_dev, double* cam_t_dev, double* pts_dev);
 /* Reduced system buffer, ba_system_size(n_opt_cam) doubles, see layout above. */
 int ba_bind_system(ba_handle h, double* sys_dev);
+/* Overwrite the reduced system with a caller-supplied packed system (HOST, ba_system_size
+ * doubles): what solve_motion_normal_eqns(S, b, mask) does with its arguments
+ * (bundle_adjuster.py:281-290).  The next ba_solve factors exactly this system, on this rank. */
+int ba_upload_system(ba_handle h, const double* packed_host, void* stream);
+/* The reduced system as compute_schur_complement returns it (bundle_adjuster.py:247-278), packed,
+ * to HOST memory (synchronises): after ba_allreduce_system the all-reduced copy, otherwise the
+ * bound buffer. */
+int ba_get_system(ba_handle h, double* packed_host, size_t count, void* stream);
+/* Tuning / robustness knobs (BA_OPT_*). */
+int ba_set_option(ba_handle h, int option, double value);
 
 /* prepare_schur_complement + apply_damping + compute_schur_complement in one pass over the
  * observations (bundle_adjuster.py:211-234, :238-242, :247-278).  Zeroes and accumulates the
@@ -134,7 +161,8 @@ int ba_cost(ba_handle h, void* stream);
 int ba_accept(ba_handle h);
 
 /* Blocks until the stream is idle, then returns cost, candidate cost and the solver status
- * (BA_OK or BA_ERR_ILLCONDITIONED).  The only synchronising call on the product path. */
+ * (BA_OK, BA_ERR_ILLCONDITIONED, BA_ERR_TIMEOUT, or BA_ERR_NONFINITE when a cost is NaN/Inf).
+ * The only synchronising call on the product path. */
 int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_status,
                     void* stream);
 /* One whole LM trial driven from HOST buffers -- what BundleAdjuster.compute_update
@@ -179,6 +207,14 @@ int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all);
 int ba_comm_system_ptr(ba_handle h, double** sys_dev);
 int ba_allreduce_system(ba_handle h, void* stream);
 int ba_allreduce_costs(ba_handle h, void* stream);
+/* Large reduced systems on sharded handles: 1 when the next ba_solve on a fresh local contribution
+ * (i.e. WITHOUT ba_allreduce_system in between) will run the DISTRIBUTED solve -- one launch per
+ * rank that sums the ranks' contributions tile by tile over peer memory (reduce-scatter), factors
+ * the tiles it owns, pushes each finished tile of L to every rank (all-gather) and substitutes
+ * backwards on its own copy, so every rank ends up with the same dC.  Replaces "all-reduce, then
+ * every rank factors the whole system" of SURVEY section 8e when the solve dominates (config 4).
+ * All ranks must then call ba_solve collectively. */
+int ba_dist_solve_active(ba_handle h);
 
 /* Per-observation residuals and Jacobians of the current state (bundle.py:251, :255-277),
  * for Bundle.residuals()/Jresiduals() and stage-wise parity checks. */

@@ -14,6 +14,11 @@ BA_ERR_CUDA = 2
 BA_ERR_NCCL = 3
 BA_ERR_BAD_ARGUMENT = 4
 BA_ERR_NOT_BOUND = 5
+BA_ERR_NONFINITE = 6
+BA_ERR_TIMEOUT = 7
+
+(BA_OPT_SPIN_TIMEOUT_MS, BA_OPT_STRICT_FLAGS, BA_OPT_DIST_SOLVE_MIN_TILES, BA_OPT_DIST_BAND,
+ BA_OPT_SOLVE_GRID_CAP) = range(5)
 
 BA_WANT_BLOCKS = 1
 BA_WANT_SCHUR = 2
@@ -39,6 +44,10 @@ SIGNATURES = {
     "ba_bind_state": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "ba_bind_candidate": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "ba_bind_system": (ctypes.c_int, [_vp, _vp]),
+    "ba_upload_system": (ctypes.c_int, [_vp, _vp, _vp]),
+    "ba_get_system": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    "ba_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
+    "ba_dist_solve_active": (ctypes.c_int, [_vp]),
     "ba_linearize_eliminate": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _vp]),
     "ba_solve": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_backsub_retract_cost": (ctypes.c_int, [_vp, _vp]),
@@ -102,5 +111,6 @@ def check(handle, rc, what):
     if rc == BA_ERR_BAD_ARGUMENT:
         raise AssertionError("%s: bad argument %s" % (what, detail))
     names = {BA_ERR_CUDA: "CUDA error", BA_ERR_NCCL: "NCCL error", BA_ERR_NOT_BOUND: "buffers not bound",
-             BA_ERR_ILLCONDITIONED: "ill-conditioned"}
+             BA_ERR_ILLCONDITIONED: "ill-conditioned", BA_ERR_NONFINITE: "non-finite cost",
+             BA_ERR_TIMEOUT: "a device-side wait timed out (peer lost or kernel fault)"}
     raise BAError("%s failed: %s %s" % (what, names.get(rc, "status %d" % rc), detail))

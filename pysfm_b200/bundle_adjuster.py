@@ -200,11 +200,15 @@ class BundleAdjuster(object):
         Returns (cost, candidate cost, status)."""
         p = self._problem
         p.linearize_eliminate(damping, self._rcond(), _lib.BA_WANT_SCHUR)
-        self._allreduce_system()
+        if not p.dist_solve:
+            self._allreduce_system()    # else: the solve sums the ranks' contributions tile by tile itself
         p.solve(cam_param_mask)
         p.backsub_retract_cost()
         self._allreduce_costs()
-        return p.read_scalars()
+        cost, cand, status = p.read_scalars()
+        if status == _lib.BA_ERR_TIMEOUT:
+            raise _lib.BAError("a device-side wait of the solver / a peer barrier timed out (peer lost or kernel fault)")
+        return cost, cand, status
 
     def _split_param_mask(self, param_mask):
         nc, nt = len(self.optim_camera_ids), len(self.optim_track_ids)

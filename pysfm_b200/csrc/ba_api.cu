@@ -1,6 +1,7 @@
 // C ABI of libba_b200.so -- see include/ba_b200.h for the contract and the reference
 // call sites each entry point replaces.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -28,6 +29,27 @@ int fail_cuda(Context* c, cudaError_t e, const char* where) {
     cudaError_t e__ = (call);                                \
     if (e__ != cudaSuccess) return fail_cuda((c), e__, #call); \
   } while (0)
+
+// The entry points run on the handle's device and leave the caller's current device as they found
+// it (torch follows cudaGetDevice: a handle on cuda:1 must not move the process to GPU 1).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = (err == cudaSuccess) && prev >= 0;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define BA_ON_DEVICE(h)                 \
+  DeviceGuard guard__((h)->device);     \
+  if (guard__.err != cudaSuccess) return fail_cuda((h), guard__.err, "cudaSetDevice")
 
 template <typename T>
 cudaError_t dev_alloc(T** p, size_t count) {
@@ -83,8 +105,8 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
       n_opt_pt < 0 || n_opt_pt > n_pt)
     return BA_ERR_BAD_ARGUMENT;
   *out = nullptr;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return BA_ERR_CUDA;
+  DeviceGuard guard__(device);
+  if (guard__.err != cudaSuccess) return BA_ERR_CUDA;
   ba_context* c = new (std::nothrow) ba_context();
   if (!c) return BA_ERR_CUDA;
   c->device = device;
@@ -111,6 +133,7 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->LinvT, T * ba::kSolveTile * ba::kSolveTile) == cudaSuccess &&
             dev_alloc(&c->solve_flags, ba::solve_flag_count((int)T)) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
+            dev_alloc(&c->solve_abort, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->cam_mask, (size_t)c->ld) == cudaSuccess &&
@@ -132,10 +155,10 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
 
 int ba_destroy(ba_handle h) {
   if (!h) return BA_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard__(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->Adense, h->LinvT, h->solve_flags, h->solve_tickets};
+                  h->Adense, h->LinvT, h->solve_flags, h->solve_tickets, h->solve_abort, h->dist_tasks};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
@@ -153,8 +176,11 @@ int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_o
     return BA_ERR_BAD_ARGUMENT;
   if (h->comm_buf) { h->last_error = "ba_comm_create called twice"; return BA_ERR_BAD_ARGUMENT; }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  BA_CUDA(h, cudaSetDevice(h->device));
-  BA_CUDA(h, dev_alloc(&h->comm_buf, ba::comm_doubles(h->sys_len)));
+  BA_ON_DEVICE(h);
+  // [contrib | reduced | costs | flags] of the collectives, then the section of the distributed solve
+  const size_t comm_len = (ba::comm_doubles(h->sys_len) + 31) & ~(size_t)31;
+  BA_CUDA(h, dev_alloc(&h->comm_buf, comm_len + ba::dist_layout(h->ld).total));
+  h->dist_off = comm_len;
   BA_CUDA(h, dev_alloc(&h->comm_done, (size_t)1));
   cudaIpcMemHandle_t mh;
   BA_CUDA(h, cudaIpcGetMemHandle(&mh, h->comm_buf));
@@ -169,7 +195,7 @@ int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_o
 
 int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all) {
   if (!h || !ipc_handles_all || !h->comm_buf) return BA_ERR_BAD_ARGUMENT;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   for (int p = 0; p < h->comm_world; ++p) {
     if (p == h->comm_rank) continue;
     cudaIpcMemHandle_t mh;
@@ -192,16 +218,16 @@ int ba_allreduce_system(ba_handle h, void* stream) {
   if (!h->comm_buf) return BA_ERR_NOT_BOUND;
   for (int p = 0; p < h->comm_world; ++p)
     if (!h->comm_peer[p]) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_peer_allreduce_system(*h, (cudaStream_t)stream));
-  h->sys_reduced = true;
+  h->sys_state = ba::kSysReduced;
   return BA_OK;
 }
 
 int ba_allreduce_costs(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!h->comm_buf) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_peer_allreduce_costs(*h, (cudaStream_t)stream));
   return BA_OK;
 }
@@ -245,18 +271,69 @@ int ba_bind_system(ba_handle h, double* sys) {
   if (!h || !sys) return BA_ERR_BAD_ARGUMENT;
   if (((size_t)sys & 15) != 0) { h->last_error = "sys must be 16-byte aligned"; return BA_ERR_BAD_ARGUMENT; }
   h->sys = sys;
+  h->sys_state = ba::kSysLocal;
   return BA_OK;
+}
+
+int ba_upload_system(ba_handle h, const double* packed_host, void* stream) {
+  if (!h || !packed_host) return BA_ERR_BAD_ARGUMENT;
+  if (!h->sys) return BA_ERR_NOT_BOUND;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_ON_DEVICE(h);
+  if (h->sys_len)
+    BA_CUDA(h, cudaMemcpyAsync(h->sys, packed_host, h->sys_len * sizeof(double), cudaMemcpyHostToDevice, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  h->sys_state = ba::kSysUploaded;   // solved as is, on this rank (not the stale all-reduced copy)
+  return BA_OK;
+}
+
+int ba_get_system(ba_handle h, double* packed_host, size_t count, void* stream) {
+  if (!h || !packed_host) return BA_ERR_BAD_ARGUMENT;
+  if (!h->sys) return BA_ERR_NOT_BOUND;
+  if (count != h->sys_len) { h->last_error = "ba_get_system: wrong element count"; return BA_ERR_BAD_ARGUMENT; }
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_ON_DEVICE(h);
+  const double* src = (h->sys_state == ba::kSysReduced && h->comm_buf) ? h->comm_buf + ba::comm_pad(h->sys_len) : h->sys;
+  if (count) BA_CUDA(h, cudaMemcpyAsync(packed_host, src, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+int ba_set_option(ba_handle h, int option, double value) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  switch (option) {
+    case BA_OPT_SPIN_TIMEOUT_MS: if (!(value > 0.0)) return BA_ERR_BAD_ARGUMENT; h->spin_timeout_ms = value; break;
+    case BA_OPT_STRICT_FLAGS: h->strict_flags = value != 0.0; break;
+    case BA_OPT_DIST_SOLVE_MIN_TILES: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->dist_min_tiles = (int)value; break;
+    case BA_OPT_DIST_BAND:
+      if (value < 1.0 || value > 64.0) return BA_ERR_BAD_ARGUMENT;
+      if (h->dist_tasks) { h->last_error = "BA_OPT_DIST_BAND must be set before the first distributed solve"; return BA_ERR_BAD_ARGUMENT; }
+      h->dist_band = (int)value;
+      break;
+    case BA_OPT_SOLVE_GRID_CAP: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->solve_grid_cap = (int)value; break;
+    default: return BA_ERR_BAD_ARGUMENT;
+  }
+  return BA_OK;
+}
+
+int ba_dist_solve_active(ba_handle h) {
+  if (!h) return 0;
+  ba::Context probe = *h;          // the question is about a FRESH local contribution
+  probe.sys_state = ba::kSysLocal;
+  for (int p = 0; p < probe.comm_world; ++p)
+    if (!probe.comm_peer[p]) return 0;
+  return ba::dist_solve_selected(probe) ? 1 : 0;
 }
 
 int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int flags, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || ((flags & BA_WANT_SCHUR) && !h->sys)) return BA_ERR_NOT_BOUND;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   int rc = ensure_track_len(*h, st);
   if (rc != BA_OK) return rc;
   if ((flags & BA_WANT_BLOCKS) && !h->W) BA_CUDA(h, dev_alloc(&h->W, (size_t)h->n_obs * 18));
-  if (flags & BA_WANT_SCHUR) h->sys_reduced = false;   // a fresh local contribution
+  if (flags & BA_WANT_SCHUR) h->sys_state = ba::kSysLocal;   // a fresh local contribution
   cudaError_t e = ba::launch_linearize_eliminate(*h, damping, pinv_rcond, flags, st);
   BA_CUDA(h, e);
   return BA_OK;
@@ -266,7 +343,7 @@ int ba_solve(ba_handle h, const unsigned char* mask_host, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!h->sys) return BA_ERR_NOT_BOUND;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (mask_host && h->n_sys > 0)
     BA_CUDA(h, cudaMemcpyAsync(h->cam_mask, mask_host, (size_t)h->n_sys, cudaMemcpyHostToDevice, st));
   BA_CUDA(h, ba::launch_solve(*h, mask_host != nullptr, st));
@@ -276,7 +353,7 @@ int ba_solve(ba_handle h, const unsigned char* mask_host, void* stream) {
 int ba_backsub_retract_cost(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_backsub_retract_cost(*h, (cudaStream_t)stream));
   return BA_OK;
 }
@@ -284,7 +361,7 @@ int ba_backsub_retract_cost(ba_handle h, void* stream) {
 int ba_cost(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h)) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_cost(*h, (cudaStream_t)stream));
   return BA_OK;
 }
@@ -301,13 +378,18 @@ int ba_accept(ba_handle h) {
 int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_status, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   ba::Scalars s;
   BA_CUDA(h, cudaMemcpyAsync(&s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, st));
   BA_CUDA(h, cudaStreamSynchronize(st));
   if (cost) *cost = s.cost;
   if (cand_cost) *cand_cost = s.cand_cost;
-  if (solve_status) *solve_status = (s.status != 0.0) ? BA_ERR_ILLCONDITIONED : BA_OK;
+  if (solve_status) {
+    // 2 = a spin-wait gave up; 1 = non-positive pivot; a NaN/Inf cost is reported as well (the
+    // reference's drivers run under numpy.seterr(all='raise'), window_slam.py:70)
+    *solve_status = (s.status == 2.0) ? BA_ERR_TIMEOUT : (s.status != 0.0) ? BA_ERR_ILLCONDITIONED :
+                    !(isfinite(s.cost) && isfinite(s.cand_cost)) ? BA_ERR_NONFINITE : BA_OK;
+  }
   return BA_OK;
 }
 
@@ -318,7 +400,7 @@ int ba_trial_host(ba_handle h, const double* cam_R_host, const double* cam_t_hos
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || !h->sys || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (cam_R_host)
     BA_CUDA(h, cudaMemcpyAsync(h->state.cam_R, cam_R_host, (size_t)h->n_cam * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
   if (cam_t_host)
@@ -341,7 +423,7 @@ int ba_trial_host_packed(ba_handle h, const double* in_host, double damping, dou
   if (!h || !out_host) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || !h->sys || !h->cand.cam_R || !h->cand.cam_t || !h->cand.pts) return BA_ERR_NOT_BOUND;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   const size_t nR = (size_t)h->n_cam * 9, nt = (size_t)h->n_cam * 3, nx = (size_t)h->n_pt * 3;
   if (in_host) {
     if (h->state.cam_t == h->state.cam_R + nR && h->state.pts == h->state.cam_t + nt) {
@@ -370,7 +452,7 @@ int ba_scalars_ptr(ba_handle h, double** p) {
 int ba_eval_observations(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h)) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (!h->obs_r) {
     BA_CUDA(h, dev_alloc(&h->obs_r, (size_t)h->n_obs * 2));
     BA_CUDA(h, dev_alloc(&h->obs_Jc, (size_t)h->n_obs * 12));
@@ -401,7 +483,7 @@ int ba_get_array(ba_handle h, int which, double* dst, size_t count, void* stream
   if (!src) return BA_ERR_NOT_BOUND;
   if (count != n) { h->last_error = "ba_get_array: wrong element count"; return BA_ERR_BAD_ARGUMENT; }
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (n) BA_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   BA_CUDA(h, cudaStreamSynchronize(st));
   return BA_OK;
@@ -411,7 +493,7 @@ int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || !h->cand.cam_R) return BA_ERR_NOT_BOUND;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (delta_cam_host && h->n_opt_cam)
     BA_CUDA(h, cudaMemcpyAsync(h->delta_cam, delta_cam_host, (size_t)h->n_opt_cam * 6 * sizeof(double),
                                cudaMemcpyHostToDevice, st));
@@ -425,7 +507,7 @@ int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt
 int ba_triangulate(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h)) return BA_ERR_NOT_BOUND;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_triangulate(*h, (cudaStream_t)stream));
   return BA_OK;
 }
@@ -433,7 +515,7 @@ int ba_triangulate(ba_handle h, void* stream) {
 int ba_set_solution(ba_handle h, const double* dC_host, void* stream) {
   if (!h || !dC_host) return BA_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   if (h->n_sys)
     BA_CUDA(h, cudaMemcpyAsync(h->dC, dC_host, (size_t)h->n_sys * sizeof(double), cudaMemcpyHostToDevice, st));
   BA_CUDA(h, cudaStreamSynchronize(st));
@@ -442,7 +524,7 @@ int ba_set_solution(ba_handle h, const double* dC_host, void* stream) {
 
 int ba_sync(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
-  BA_CUDA(h, cudaSetDevice(h->device));
+  BA_ON_DEVICE(h);
   BA_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
   return BA_OK;
 }

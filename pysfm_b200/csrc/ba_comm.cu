@@ -3,7 +3,9 @@
 // Every rank owns one IPC-exported device buffer:
 //     contrib [sys_len]   its own packed reduced system (the elimination kernel reduces into it)
 //     reduced [sys_len]   the all-reduced system (peers push their slices here; the solver reads it)
-//     costs   [world][2]  {cost, candidate cost} of every rank (pushed by the ranks)
+//     costs   [2][world][2]  {cost, candidate cost} of every rank (pushed by the ranks), two banks
+//                         used in turn (epoch parity): a fast rank's next reduction cannot
+//                         overwrite values a slower rank has not summed yet
 //     flags   [3][world]  arrival flags of the three barriers (epoch valued, never reset)
 // and maps the buffers of all peers (NVLink 5 / NVSwitch: every peer at full bandwidth).
 //
@@ -42,13 +44,33 @@ struct PeerArgs {
   size_t lo, hi;             // this rank's slice [lo, hi) of the packed system (even bounds)
   unsigned int epoch;
   unsigned int* done;        // local CTA counter (last-CTA-done)
+  double* status;            // local scalar status word: 2 when a barrier ran past its deadline
+  unsigned long long spin_limit_ns;
 };
+
+__device__ __forceinline__ unsigned long long comm_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait for *f to reach the epoch; gives up (status 2 -> BA_ERR_TIMEOUT) when a peer never arrives
+__device__ __forceinline__ void wait_arrival(const PeerArgs& g, const unsigned int* f) {
+  const unsigned long long t0 = comm_ns();
+  unsigned int spins = 0;
+  while ((int)(ld_acquire_sys(f) - g.epoch) < 0) {
+    if ((++spins & 255u) == 0u && comm_ns() - t0 > g.spin_limit_ns) {
+      *g.status = 2.0;
+      break;
+    }
+    __nanosleep(40);
+  }
+}
 
 __device__ __forceinline__ double* contrib_of(double* base) { return base; }
 __device__ __forceinline__ double* reduced_of(double* base, size_t sys_len) { return base + comm_pad(sys_len); }
 __device__ __forceinline__ double* costs_of(double* base, size_t sys_len) { return base + 2 * comm_pad(sys_len); }
 __device__ __forceinline__ unsigned int* flags_of(double* base, size_t sys_len) {
-  return reinterpret_cast<unsigned int*>(base + 2 * comm_pad(sys_len) + 2 * kMaxPeers);
+  return reinterpret_cast<unsigned int*>(base + 2 * comm_pad(sys_len) + 4 * kMaxPeers);
 }
 
 // signal barrier `which` to every rank, then wait until every rank has signalled us
@@ -56,8 +78,7 @@ __device__ __forceinline__ void peer_barrier(const PeerArgs& g, int which, int l
   if (lane_in_block < g.world) {
     __threadfence_system();
     st_release_sys(flags_of(g.base[lane_in_block], g.sys_len) + which * kMaxPeers + g.rank, g.epoch);
-    const unsigned int* mine = flags_of(g.base[g.rank], g.sys_len) + which * kMaxPeers + lane_in_block;
-    while ((int)(ld_acquire_sys(mine) - g.epoch) < 0) __nanosleep(40);
+    wait_arrival(g, flags_of(g.base[g.rank], g.sys_len) + which * kMaxPeers + lane_in_block);
   }
 }
 
@@ -70,10 +91,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_system_kernel(const PeerAr
     __threadfence_system();
     st_release_sys(flags_of(g.base[tid], g.sys_len) + 0 * kMaxPeers + g.rank, g.epoch);
   }
-  if (tid < g.world) {
-    const unsigned int* mine = flags_of(g.base[g.rank], g.sys_len) + 0 * kMaxPeers + tid;
-    while ((int)(ld_acquire_sys(mine) - g.epoch) < 0) __nanosleep(40);
-  }
+  if (tid < g.world) wait_arrival(g, flags_of(g.base[g.rank], g.sys_len) + 0 * kMaxPeers + tid);
   __syncthreads();
   // ---- reduce my slice over all ranks (rank order), push it to everybody -----------------------
   // all peers' loads of an element are in flight together (NVLink round trip ~1 us), then the sum
@@ -106,15 +124,16 @@ __global__ void __launch_bounds__(256) peer_allreduce_system_kernel(const PeerAr
 
 __global__ void peer_allreduce_costs_kernel(const PeerArgs g, Scalars* sc) {
   const int tid = threadIdx.x;
+  const int bank = (int)(g.epoch & 1u) * 2 * kMaxPeers;
   if (tid < g.world) {
-    double* c = costs_of(g.base[tid], g.sys_len) + 2 * g.rank;
+    double* c = costs_of(g.base[tid], g.sys_len) + bank + 2 * g.rank;
     c[0] = sc->cost;
     c[1] = sc->cand_cost;
   }
   peer_barrier(g, 2, tid);
   __syncwarp();
   if (tid == 0) {
-    const volatile double* c = costs_of(g.base[g.rank], g.sys_len);
+    const volatile double* c = costs_of(g.base[g.rank], g.sys_len) + bank;
     double a = 0.0, b = 0.0;
     for (int p = 0; p < g.world; ++p) { a += c[2 * p]; b += c[2 * p + 1]; }
     sc->cost = a;
@@ -133,6 +152,8 @@ static PeerArgs make_peer_args(Context& c) {
   g.hi = g.lo + chunk < padded ? g.lo + chunk : padded;
   g.epoch = ++c.comm_epoch;
   g.done = c.comm_done;
+  g.status = &c.scalars->status;
+  g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
   return g;
 }
 

@@ -16,9 +16,41 @@ __host__ __device__ inline size_t solve_rowflag_base(int T) { return ((size_t)T 
 inline size_t solve_flag_count(int T) { return solve_rowflag_base(T) + 8 * (size_t)T + 8 * (size_t)T * T; }
 
 // doubles reserved per section of the peer-visible comm buffer (even, so that sections stay
-// 16-byte aligned): [contrib | reduced | costs 2*kMaxPeers | flags 3*kMaxPeers u32]
+// 16-byte aligned): [contrib | reduced | costs 2 banks x 2*kMaxPeers | flags 3*kMaxPeers u32]
 __host__ __device__ inline size_t comm_pad(size_t sys_len) { return (sys_len + 2 + 31) & ~(size_t)31; }
-inline size_t comm_doubles(size_t sys_len) { return 2 * comm_pad(sys_len) + 2 * kMaxPeers + (3 * kMaxPeers + 1) / 2 + 2; }
+inline size_t comm_doubles(size_t sys_len) { return 2 * comm_pad(sys_len) + 4 * kMaxPeers + (3 * kMaxPeers + 1) / 2 + 2; }
+
+// Distributed reduced solve (ba_solve.cu, DIST): peer-visible section of every rank, placed behind
+// the comm sections in the same IPC-exported allocation.  Offsets in doubles from the section base:
+//   contrib [ld*ld + ld]   this rank's dense lower-triangular contribution + its rhs (expand_system_kernel)
+//   L       [ld*ld + ld]   the factor, replicated: every tile is computed by ONE rank and pushed to all; rhs -> y
+//   LinvT   [T][64*64]     transposed inverses of the diagonal tiles (pushed row block by row block)
+//   flags   [solve_flag_count(T)] u32, same layout as the single-GPU solver's, written by the tile owners
+//   bar     [kMaxPeers] u32  start barrier (epoch valued)  | abort u32 | pad | status f64
+struct DistLayout {
+  size_t contrib, L, LinvT, flags, bar, abort, status, total;
+};
+__host__ __device__ inline DistLayout dist_layout(int ld) {
+  const size_t T = (size_t)ld / kSolveTile;
+  const size_t dense = (size_t)ld * ld + ld;
+  const size_t nflags = solve_rowflag_base((int)T) + 8 * T + 8 * T * T;
+  DistLayout d;
+  d.contrib = 0;
+  d.L = d.contrib + ((dense + 1) & ~(size_t)1);
+  d.LinvT = d.L + ((dense + 1) & ~(size_t)1);
+  d.flags = d.LinvT + T * kSolveTile * kSolveTile;
+  d.bar = d.flags + (((nflags + 3) / 2) & ~(size_t)1);
+  d.abort = d.bar + kMaxPeers / 2;
+  d.status = d.abort + 2;
+  d.total = d.status + 2;
+  return d;
+}
+
+// state of the packed reduced system of a handle
+enum { kSysLocal = 0,     // this rank's contribution (fresh from the elimination kernel)
+       kSysReduced = 1,   // all-reduced by ba_allreduce_system: the `reduced` section of the comm buffer
+       kSysUploaded = 2   // overwritten by the caller (ba_upload_system): solved as is, locally
+};
 
 struct ParamSet {   // caller-owned device arrays
   double* cam_R = nullptr;  // [n_cam][9]
@@ -93,7 +125,20 @@ struct Context {
   double* comm_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned int* comm_done = nullptr;        // last-CTA-done counter of the all-reduce kernel
   unsigned int comm_epoch = 0;
-  bool sys_reduced = false;                 // the solver reads the all-reduced copy
+  int sys_state = kSysLocal;                // what the bound system holds (which copy the solver reads)
+  // distributed reduced solve (tiles owned by ranks, operands exchanged over peer memory)
+  size_t dist_off = 0;                      // doubles from comm_buf to the rank's DistLayout section (0 = none)
+  int* dist_tasks = nullptr;                // this rank's tile tasks in global ticket order ((i << 16) | j; chain C_j = (j, j))
+  int dist_ntasks = 0;
+  unsigned int dist_epoch = 0;
+  int dist_min_tiles = 32;                  // BA_OPT_DIST_SOLVE_MIN_TILES: distributed solve when ld/64 >= this (0 = never)
+  int dist_band = 2;                        // BA_OPT_DIST_BAND: tiles with i - j <= band stay on rank 0 with the chain tasks
+  bool dist_attr_set = false;
+  // robustness knobs of the spin-waits (solver flags, peer barriers)
+  double spin_timeout_ms = 10000.0;         // BA_OPT_SPIN_TIMEOUT_MS
+  int strict_flags = 0;                     // BA_OPT_STRICT_FLAGS: release/acquire flag publication in the solver
+  int solve_grid_cap = 0;                   // BA_OPT_SOLVE_GRID_CAP: at most this many solver CTAs (0 = one per SM)
+  unsigned int* solve_abort = nullptr;      // [1] set by a spin-wait that ran past the deadline
 
   long long launches = 0;
   std::string last_error;
@@ -110,5 +155,6 @@ cudaError_t launch_triangulate(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
+bool dist_solve_selected(const Context& c);
 
 }  // namespace ba

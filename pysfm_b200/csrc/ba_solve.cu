@@ -39,6 +39,11 @@
 //                          the measured timeline and what bounds it.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <utility>
+#include <vector>
 
 #include "ba_context.h"
 
@@ -61,7 +66,8 @@ __global__ void __launch_bounds__(256)
 expand_system_kernel(const double* __restrict__ packed, int nc, int n_sys, int ld,
                      const unsigned char* __restrict__ mask, bool have_mask,
                      double* __restrict__ A, double* __restrict__ rhs,
-                     unsigned int* __restrict__ tickets, double* __restrict__ status, double* __restrict__ x) {
+                     unsigned int* __restrict__ tickets, double* __restrict__ status, double* __restrict__ x,
+                     unsigned int* __restrict__ abort_word, double* __restrict__ dist_status, double unit_diag) {
   const int q = blockIdx.x;  // column
   // the solution vector starts out as "not there yet": the backward substitution polls the data itself
   if (threadIdx.x == 0) x[q] = __longlong_as_double(kNotYet);
@@ -69,11 +75,15 @@ expand_system_kernel(const double* __restrict__ packed, int nc, int n_sys, int l
     tickets[0] = 0u;
     tickets[1] = 0u;
     *status = 0.0;
+    *abort_word = 0u;
+    if (dist_status) *dist_status = 0.0;
   }
   const bool free_q = q < n_sys && (!have_mask || mask[q]);
   double* col = A + (size_t)q * ld;
   if (!free_q) {
-    for (int p = q + threadIdx.x; p < ld; p += blockDim.x) col[p] = (p == q) ? 1.0 : 0.0;
+    // unit_diag: 1 on a single GPU; in the distributed solve the ranks' contributions are summed,
+    // so only rank 0 contributes the unit pivot of a frozen / padding parameter
+    for (int p = q + threadIdx.x; p < ld; p += blockDim.x) col[p] = (p == q) ? unit_diag : 0.0;
     if (threadIdx.x == 0) rhs[q] = 0.0;
     return;
   }
@@ -118,6 +128,39 @@ __device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
 }
 __device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// System-scope variants: in the distributed solve the flags of a rank are written by its peers
+// over NVLink, so both sides of every flag use .sys (a .gpu load is not morally strong against
+// a store of another GPU).
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {   // peer memory: never cached on this side
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+template <bool SYS>
+__device__ __forceinline__ unsigned int ldf_acquire(const unsigned int* p) { return SYS ? ld_acquire_sys(p) : ld_acquire(p); }
+template <bool SYS>
+__device__ __forceinline__ unsigned int ldf_relaxed(const unsigned int* p) { return SYS ? ld_relaxed_sys(p) : ld_relaxed(p); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 // Column m of a k-major shared tile (64 contiguous doubles at tile + m*LDT) to the global tile
 // (column m at dst + m*ld) as ONE bulk copy on the TMA path, own bulk group; bulk_store_wait()
@@ -202,15 +245,52 @@ struct CholArgs {
   double* __restrict__ LinvT;     // [T][NB*NB]  LinvT[m*NB + c] = (L_jj^{-1})[c][m]
   unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready ; [T*T + 10T + 8(iT+j) + b] columns 8b.. of L_ij ready
   unsigned int* __restrict__ tickets; // [0] tile tasks, [1] back-substitution tasks
-  double* __restrict__ status;    // set to 1 on a non-positive pivot
+  double* __restrict__ status;    // set to 1 on a non-positive pivot, 2 when a spin-wait ran past the deadline
   int ld, T;
   unsigned int epoch;
+  // ---- robustness ----
+  unsigned int* __restrict__ abort;   // [1] != 0: some spin-wait (here or on a peer) gave up; every wait falls through
+  unsigned long long spin_limit_ns;   // budget of the whole launch for waiting
+  int strict;                         // release/acquire publication of the column-block flags (PTX-model clean, slower)
+  // ---- distributed mode (DIST): tiles are owned by ranks, see the header of the kernel ----
+  int world, rank;
+  const int* __restrict__ tasks;      // this rank's tasks in global ticket order: (i << 16) | j, chain task C_j as (j, j)
+  int ntasks;
+  double* base[kMaxPeers];            // DistLayout section of every rank (own rank included), peer-mapped
 };
 
+__device__ __forceinline__ void raise_abort(const CholArgs& g) {
+  atomicExch(g.abort, 1u);
+  *g.status = 2.0;
+  if (g.world > 1) {
+    const DistLayout d = dist_layout(g.ld);
+    for (int p = 0; p < g.world; ++p)
+      if (p != g.rank) st_relaxed_sys(reinterpret_cast<unsigned int*>(g.base[p] + d.abort), 1u);
+  }
+}
+// Called on the idle path of every polling loop.  true = stop waiting: this launch (or a peer's)
+// has spent its waiting budget -- a peer died, a kernel faulted, or a flag was lost.  The task
+// then runs on with whatever is there (finite garbage), the launch ends, status 2 is reported.
+__device__ __forceinline__ bool spin_expired(const CholArgs& g, unsigned int& spins, const unsigned long long& t0) {
+  if ((++spins & 63u) != 0u) return false;
+  if (ld_relaxed_sys(g.abort) != 0u) {
+    *g.status = 2.0;
+    return true;
+  }
+  if (global_ns() - t0 < g.spin_limit_ns) return false;
+  raise_abort(g);
+  return true;
+}
+
 // Block-wide wait until *f == epoch (thread 0 spins with acquire loads).
-__device__ __forceinline__ void wait_flag(const unsigned int* f, unsigned int epoch) {
+template <bool SYS>
+__device__ __forceinline__ void wait_flag(const CholArgs& g, const unsigned int* f, unsigned int epoch, const unsigned long long& t0) {
   if (threadIdx.x == 0) {
-    while (ld_acquire(f) != epoch) __nanosleep(20);
+    unsigned int spins = 0;
+    while (ldf_acquire<SYS>(f) != epoch) {
+      if (spin_expired(g, spins, t0)) break;
+      __nanosleep(20);
+    }
   }
 }
 
@@ -353,6 +433,20 @@ constexpr int TD = 8 * TS;
 constexpr int kSolveSmemDoubles = 4 * kTileDoubles + 8 * NB;
 constexpr size_t kSolveSmemBytes = kSolveSmemDoubles * sizeof(double);
 
+// DIST (points sharded over the GPUs of one node, large reduced systems): ONE launch per rank
+// does the reduce-scatter of the ranks' contributions, the factorisation and the all-gather of
+// the factor, tile by tile, over NVLink peer memory:
+//   * every tile task has ONE owner rank (g.tasks: the rank's tasks in global ticket order).  The
+//     chain tasks and the band next to the diagonal stay on rank 0, so the critical path never
+//     crosses a link; the rest of row i belongs to one rank, so a row's tile-to-tile dependency
+//     (L_ij is the last operand of task (i, j+1)) stays local and progressive.
+//   * the owner sums A_ij over the ranks' dense contributions (peer loads in rank order, one peer
+//     per step of the k loop, so the link latency hides behind the tile products),
+//   * and pushes the finished L_ij (bulk copies shared -> peer global), the rows of Linv_jj and
+//     y_j to EVERY rank, followed by the tile's flags (system-scope release): every rank ends up
+//     with the whole factor and runs the backward substitution on its own copy -- all ranks get
+//     the same bits for dC without a broadcast.
+template <bool DIST>
 __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const CholArgs g) {
   extern __shared__ __align__(16) double sm[];
   double* const buf = sm;
@@ -362,14 +456,35 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   __shared__ int s_task;
   __shared__ __align__(16) unsigned int s_snap[8];   // asynchronous snapshot of the 8 row-block flags a task polls
   __shared__ int s_bad;
+  __shared__ unsigned long long s_t0;   // start of the launch: the waiting budget counts from here
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   const int gq = lane >> 2, t4 = lane & 3;
   const int R0 = 32 * (wid & 1), C0 = 16 * (wid >> 1);
   const int T = g.T;
   const size_t ld = (size_t)g.ld;
-  const int ntasks = 1 + T * (T - 1) / 2;   // chain task C_0, then per column one chain + the panels below
+  const int ntasks = DIST ? g.ntasks : 1 + T * (T - 1) / 2;   // chain task C_0, then per column one chain + the panels below
   const unsigned int epoch = g.epoch;
+  const DistLayout dl = dist_layout(g.ld);
+  if (tid == 0) s_t0 = global_ns();
+  __syncthreads();
+  if (DIST) {
+    // start barrier: every rank's contribution is expanded (its expand kernel precedes this launch
+    // in its stream) and nobody is still inside the previous solve; nothing is pushed before it
+    if (blockIdx.x == 0 && tid < g.world) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<unsigned int*>(g.base[tid] + dl.bar) + g.rank, epoch);
+    }
+    if (tid < g.world) {
+      const unsigned int* mine = reinterpret_cast<const unsigned int*>(g.base[g.rank] + dl.bar) + tid;
+      unsigned int spins = 0;
+      while (ld_acquire_sys(mine) != epoch) {
+        if (spin_expired(g, spins, s_t0)) break;
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
 
   // ======================================= factorisation ===================================
   // Ticket order:  C_0;  then per column j = 0 .. T-2:  C_{j+1}, (j+2, j), ..., (T-1, j).
@@ -395,7 +510,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     bool chain = true;
     int j = 0;          // chain: diagonal tile index;  panel: column
     int pi = 0, pj = 0; // the panel tile (pi, pj) of this task (chain: (j, j - 1))
-    if (t > 0) {
+    if (DIST) {
+      const int code = g.tasks[t];
+      pi = code >> 16;
+      pj = code & 0xffff;
+      chain = (pi == pj);
+      j = pj;
+      if (chain && j > 0) pj = j - 1;
+    } else if (t > 0) {
       // column-major enumeration over columns 0 .. T-2, column jc holding T-1-jc tasks
       const int tt = t - 1;
       const double Tf = (double)Tm + 0.5;
@@ -410,7 +532,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       pi = jc + 1 + rem;
       pj = jc;
     }
-    const bool has_panel = t > 0;
+    const bool has_panel = DIST ? !(chain && j == 0) : t > 0;
     BA_TRACE_SET(t, 0, ((unsigned long long)(chain ? j : pi) << 32) | (unsigned)(chain ? j : pj));
     BA_TRACE_SET(t, 1, (unsigned long long)blockIdx.x);
     BA_TRACE(t, 2);   // task grabbed
@@ -420,7 +542,31 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     Frag acc;            // panel tile  A_{pi,pj} - sum_k L_{pi,k} L_{pj,k}^T   (warp tile R0, C0)
     RowTiles W;          // diagonal tile A_jj - sum_k L_jk L_jk^T, lower triangle, row-block owned
     acc.zero();
-    if (has_panel) {
+    // DIST: the original tile is the sum of the ranks' contributions.  Peer p's share of the panel
+    // tile is fetched at step p of the k loop and added after that step's products (fixed order:
+    // the result does not depend on timing); what the k loop is too short for follows after it.
+    const size_t tile_off = (size_t)(pj * NB) * ld + (size_t)pi * NB;
+    auto contrib_load = [&](int p, Frag& c) {
+      const double* Ap = g.base[p] + dl.contrib + tile_off;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
+            c.v[mi][ni][e] = ld_peer_f64(Ap + (size_t)cc * ld + rr);
+          }
+    };
+    auto contrib_add = [&](const Frag& c) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += c.v[mi][ni][e];
+    };
+    if (!DIST && has_panel) {
       const double* Ap = g.A + (size_t)(pj * NB) * ld + (size_t)pi * NB;
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
@@ -435,7 +581,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     double bacc = 0.0, rhs_j = 0.0;   // tid < NB: sum_k (L_jk y_k)[tid], b_j
 #pragma unroll
     for (int c = 0; c < 8; ++c) W.t[c][0] = W.t[c][1] = 0.0;
-    if (chain) {
+    if (!DIST && chain) {
       const double* Ajj = g.A + (size_t)(j * NB) * ld + (size_t)j * NB;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -447,6 +593,26 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
       if (tid < NB) rhs_j = __ldcg(g.rhs + j * NB + tid);
     }
+    if (DIST && chain) {
+      // diagonal tile and right-hand side: summed here, in rank order.  A chain task is grabbed
+      // well before its last operand exists, so these round trips are off the critical path.
+      for (int p = 0; p < g.world; ++p) {
+        const double* Ajj = g.base[p] + dl.contrib + (size_t)(j * NB) * ld + (size_t)j * NB;
+        double w[8][2];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int row = 8 * r + gq, col = 8 * c + 2 * t4 + e;
+            const int hi = row > col ? row : col, lo = row > col ? col : row;
+            w[c][e] = (c <= r) ? ld_peer_f64(Ajj + (size_t)lo * ld + hi) : 0.0;
+          }
+        const double rb = (tid < NB) ? ld_peer_f64(g.base[p] + dl.contrib + ld * ld + j * NB + tid) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { W.t[c][0] += w[c][0]; W.t[c][1] += w[c][1]; }
+        rhs_j += rb;
+      }
+    }
 
     // ---- k loop over the finished columns k < pj:  P = L_{pi,k}, Q = L_{pj,k} ------------------
     auto issue = [&](int k) {
@@ -456,9 +622,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       cp_async_commit();
     };
     auto wait_k = [&](int k) {
-      wait_flag(&g.flags[(size_t)pi * T + k], epoch);
-      wait_flag(&g.flags[(size_t)pj * T + k], epoch);
-      if (chain) wait_flag(&yflag[k], epoch);
+      wait_flag<DIST>(g, &g.flags[(size_t)pi * T + k], epoch, s_t0);
+      wait_flag<DIST>(g, &g.flags[(size_t)pj * T + k], epoch, s_t0);
+      if (chain) wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
     };
     // The tiles of step k+1 are prefetched while step k computes ONLY if they are already
     // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
@@ -487,16 +653,16 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             const int kk = k + 1 + lane;
             bool ok = false;
             if (lane < 8 && kk < kfull) {
-              const unsigned int f0 = ld_relaxed(&g.flags[(size_t)pi * T + kk]);
-              const unsigned int f1 = ld_relaxed(&g.flags[(size_t)pj * T + kk]);
-              const unsigned int f2 = chain ? ld_relaxed(&yflag[kk]) : epoch;
+              const unsigned int f0 = ldf_relaxed<DIST>(&g.flags[(size_t)pi * T + kk]);
+              const unsigned int f1 = ldf_relaxed<DIST>(&g.flags[(size_t)pj * T + kk]);
+              const unsigned int f2 = chain ? ldf_relaxed<DIST>(&yflag[kk]) : epoch;
               ok = f0 == epoch && f1 == epoch && f2 == epoch;
             }
             const unsigned int mask = __ballot_sync(0xffffffffu, ok) & 0xffu;
             if (lane == 0) {
               const unsigned int m = ~mask & 0xffu;
               const int n = m ? __ffs(m) - 1 : 8;      // consecutive ready steps from k + 1
-              if (n > 0) __threadfence();               // acquire for what the relaxed loads saw
+              if (n > 0) { if (DIST) __threadfence_system(); else __threadfence(); }   // acquire for what the relaxed loads saw
               s_task = k + n;
             }
           }
@@ -514,9 +680,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         cp_async_wait<0>();
       }
       if (chain && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
+      Frag ctmp;
+      const bool cadd = DIST && k < g.world;   // CTA-uniform
+      if (cadd) contrib_load(k, ctmp);
       __syncthreads();
       const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
+      if (cadd) contrib_add(ctmp);
       if (chain) {
         diag_rows_dmma(W, P, r, lane);
         if (tid < NB) {
@@ -528,8 +698,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
       __syncthreads();
     }
+    int cnext = 0;   // DIST: contributions of peers [0, cnext) are in acc
+    if (DIST) cnext = kfull < g.world ? kfull : g.world;
     if (pj > 0) {
       const int k = pj - 1;
+      Frag clast;
+      const bool cl = DIST && cnext < g.world;   // one more peer rides on the last step
+      if (cl) contrib_load(cnext, clast);
       double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       double* Q = P + kTileDoubles;
       const double* gP = g.A + (size_t)(k * NB) * ld + (size_t)pi * NB;
@@ -546,14 +721,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll 1
       while (ca < 8 || cw < 8) {
         if (tid == 0) {
+          unsigned int spins = 0;
           for (;;) {
             unsigned int f[8], h[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              f[q] = (q >= pf) ? ld_relaxed(fP + q) : epoch;
-              h[q] = (q >= ca) ? ld_relaxed(fQ + q) : epoch;
+              f[q] = (q >= pf) ? ldf_relaxed<DIST>(fP + q) : epoch;
+              h[q] = (q >= ca) ? ldf_relaxed<DIST>(fQ + q) : epoch;
             }
-            const unsigned int fy = gemv_done ? 0u : ld_relaxed(&yflag[k]);
+            const unsigned int fy = gemv_done ? 0u : ldf_relaxed<DIST>(&yflag[k]);
             int eP = 0, eQ = 0;
             bool runP = true, runQ = true;
 #pragma unroll
@@ -566,7 +742,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             const int eA = eP < eQ ? eP : eQ;
             const bool yr = !gemv_done && fy == epoch && eP == 8;
             if (eA > ca || eP > cw || yr) {
+              // acquire for what the relaxed loads saw: only on request (the operands are fetched
+              // from L2 with cp.async.cg after the flag load returned), and
+              // always across GPUs
+              if (DIST || g.strict) __threadfence_system();
               s_task = eP | (eQ << 4) | (yr ? 256 : 0);
+              break;
+            }
+            if (spin_expired(g, spins, s_t0)) {
+              s_task = 8 | (8 << 4) | (gemv_done ? 0 : 256);
               break;
             }
             __nanosleep(20);
@@ -606,7 +790,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         if (ca < eA) ca = eA;
       }
       if (!gemv_done) {
-        wait_flag(&yflag[k], epoch);
+        wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
         __syncthreads();
         if (tid < NB) {
           yk[tid] = __ldcg(g.rhs + k * NB + tid);
@@ -619,7 +803,22 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           bacc += s;
         }
       }
+      if (cl) {
+        contrib_add(clast);
+        ++cnext;
+      }
       __syncthreads();
+    }
+    if (DIST && has_panel) {
+      // peers the k loop was too short for (tasks of the first `world` columns): two round trips in
+      // flight at a time, added in rank order
+      for (; cnext < g.world; cnext += 2) {
+        Frag c0, c1;
+        contrib_load(cnext, c0);
+        if (cnext + 1 < g.world) contrib_load(cnext + 1, c1);
+        contrib_add(c0);
+        if (cnext + 1 < g.world) contrib_add(c1);
+      }
     }
     BA_TRACE(t, 3);   // k loop done
 
@@ -652,6 +851,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       int cb = 0, ub = 0;
       bool have_snap = false;   // s_snap holds (or is about to hold) a snapshot newer than the last scan
       int pub_lo = -1, pub_hi = 0;   // column blocks whose bulk copies are in flight, flags not yet set (CTA-uniform)
+      unsigned int pspins = 0;       // idle polls of the row-block flags (warp 1, lane 0)
       // column blocks [b0, b1) of Ls on their way out: at most one column per thread (issuing a bulk
       // copy costs ~25 ns and serialises inside a warp, so the issue is spread over the CTA)
       auto pub_issue = [&](int b0, int b1) {
@@ -660,7 +860,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       };
       auto pub_flags = [&]() {   // after every thread's bulk_store_wait() and a barrier
         if (pub_lo >= 0) {
-          if (wid == 0 && lane >= pub_lo && lane < pub_hi) st_relaxed(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
+          // relaxed by default: the bulk copies have COMPLETED (bulk_store_wait, not .read), i.e. the
+          // bytes are in L2, and consumers fetch from L2 after seeing the flag.  g.strict publishes
+          // with a release instead (clean under the PTX memory model; ~0.6 us of stalled memory
+          // traffic per group, tests/test_gpu_parity.py holds the two variants to the same bits)
+          if (wid == 0 && lane >= pub_lo && lane < pub_hi) {
+            unsigned int* f = colflag + ((size_t)pi * T + pj) * 8 + lane;
+            if (g.strict) st_release(f, epoch); else st_relaxed(f, epoch);
+          }
           pub_lo = -1;
         }
       };
@@ -687,7 +894,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             }
             if (fresh) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ld_relaxed(rf + q) : epoch;
+              for (int q = 0; q < 8; ++q) f[q] = (q >= cb) ? ldf_relaxed<DIST>(rf + q) : epoch;
             }
             bool run = true;
 #pragma unroll
@@ -697,7 +904,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
                 if (run) e = q + 1;
               }
             // only when nothing is ready yet, spin on the next block
-            if (e == cb) e = -1;   // nothing new: flush the pending publication, fold pending column blocks into W
+            if (e == cb) e = spin_expired(g, pspins, s_t0) ? 8 : -1;   // nothing new: flush the pending publication, fold pending column blocks into W
+            else if (DIST || g.strict) __threadfence_system();          // acquire for the rows the scan found
             s_task = e;
           }
           e = __shfl_sync(0xffffffffu, e, 0);
@@ -733,7 +941,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         bulk_store_wait();   // the previous group has had a scan and a fetch to land in L2
         __syncthreads();   // rows of blocks cb .. ce-1 of Linv (and, first time round, Cs) are in shared memory
         pub_flags();
-        if (ce < 8 && !chain) {   // snapshot of the flags for the next scan, taken under the DMMAs below
+        if (ce < 8 && !chain && !DIST) {   // snapshot of the flags for the next scan, taken under the DMMAs below
           // (panel tasks only: a chain task gains more from the larger groups a fresh scan finds)
           if (tid == 32) {
             cp_async16(s_snap, rf);
@@ -837,10 +1045,36 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       if (wid == 1) {
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
+        if (DIST) {
+          // ... and sends the whole tile, still in Ls, to every peer: 64 bulk copies (one column each)
+          // per peer on the TMA path.  A plain panel task waits for them right here and raises the
+          // tile's flags on the peers; in a chain task warp 1 does that when its row block of the
+          // sweep is finished (peer_tile_flags below), so the sweep starts without the link latency.
+          for (int p = 0; p < g.world; ++p)
+            if (p != g.rank) {
+              double* dst = g.base[p] + dl.L + tile_off;
+              bulk_store_column(dst, g.ld, Ls, lane);
+              bulk_store_column(dst, g.ld, Ls, lane + 32);
+            }
+        }
       }
       if (chain && ub < 8) fold(ub, 8);
       BA_TRACE(t, 6);   // panel part done
     }
+    // warp 1: the tile's bulk copies to the peers have landed -> release its 8 column-block flags and
+    // the tile flag on every peer (system scope)
+    auto peer_tile_flags = [&]() {
+      bulk_store_wait();
+      __threadfence_system();
+      __syncwarp();
+      for (int p = 0; p < g.world; ++p)
+        if (p != g.rank && lane < 9) {
+          unsigned int* pf = reinterpret_cast<unsigned int*>(g.base[p] + dl.flags);
+          unsigned int* f = lane < 8 ? pf + solve_rowflag_base(T) + 8 * T + ((size_t)pi * T + pj) * 8 + lane : pf + (size_t)pi * T + pj;
+          st_relaxed_sys(f, epoch);
+        }
+    };
+    if (DIST && has_panel && !chain && wid == 1) peer_tile_flags();
 
     if (chain) {
       double* const LT = g.LinvT + (size_t)j * NB * NB;
@@ -1000,6 +1234,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = mc0[c];
             LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = mc1[c];
           }
+          if (DIST) {   // the same rows straight into every peer's copy (fire and forget; flagged below)
+            for (int p = 0; p < g.world; ++p) {
+              if (p == g.rank) continue;
+              double* PT = g.base[p] + dl.LinvT + (size_t)j * NB * NB;
+              PT[(8 * pb + t4) * NB + 8 * pb + gq] = l0;
+              PT[(8 * pb + 4 + t4) * NB + 8 * pb + gq] = l1;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                if (c >= pb) break;
+                PT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = mc0[c];
+                PT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = mc1[c];
+              }
+            }
+          }
         }
         if (r == pb && pb > 0) {
           // rows 8 pb .. 8 pb + 7 of L_jj^{-1} are final and this warp has nothing left to do in
@@ -1011,6 +1259,16 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           if (pb == 1 && lane == 1) st_release(&rowflag[(size_t)j * 8 + 0], epoch);
           if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
           BA_GT(pb, t == g_dbg_producer && lane == 0);
+          if (DIST) {
+            // the peers' copies of these rows (and of row block 0, stored by warp 0 two barriers ago)
+            __threadfence_system();
+            if (lane < g.world && lane != g.rank) {
+              unsigned int* prf = reinterpret_cast<unsigned int*>(g.base[lane] + dl.flags) + solve_rowflag_base(T) + (size_t)j * 8;
+              if (pb == 1) st_relaxed_sys(prf + 0, epoch);
+              st_relaxed_sys(prf + pb, epoch);
+            }
+            if (pb == 1 && has_panel) peer_tile_flags();   // row block 1 is warp 1's: its part of the sweep is over
+          }
         }
         if (r > pb) {
           const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];
@@ -1068,12 +1326,22 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           LTs[(e >> 6) * LDT + (e & 63)] = v;
           LT[e] = v;
         }
-        __threadfence();
+        if (DIST) {
+          for (int p = 0; p < g.world; ++p) {
+            if (p == g.rank) continue;
+            double* PT = g.base[p] + dl.LinvT + (size_t)j * NB * NB;
+            for (int e = tid; e < NB * NB; e += kSolveThreads) PT[e] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+            if (tid == 0) *(g.base[p] + dl.status) = 1.0;   // every rank reports the failed pivot
+          }
+          __threadfence_system();
+        } else {
+          __threadfence();
+        }
       }
       // forward substitution: y_j = Linv (b_j - sum_{k<j} L_jk y_k); the k = j-1 term comes from
       // the panel tile this task produced itself (still in Ls)
       if (j > 0) {
-        wait_flag(&yflag[j - 1], epoch);
+        wait_flag<DIST>(g, &yflag[j - 1], epoch, s_t0);
         __syncthreads();
         if (tid < NB) yk[tid] = __ldcg(g.rhs + (j - 1) * NB + tid);
         __syncthreads();
@@ -1093,9 +1361,19 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll 8
         for (int m = 0; m < mend; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
+        if (DIST)
+          for (int p = 0; p < g.world; ++p)
+            if (p != g.rank) (g.base[p] + dl.L + ld * ld)[j * NB + tid] = s;   // every rank substitutes backwards on its own
       }
       __syncthreads();
-      if (tid == 0) st_release(&yflag[j], epoch);
+      if (tid == 0) {
+        st_release(&yflag[j], epoch);
+        if (DIST) {
+          __threadfence_system();
+          for (int p = 0; p < g.world; ++p)
+            if (p != g.rank) st_relaxed_sys(reinterpret_cast<unsigned int*>(g.base[p] + dl.flags) + (size_t)T * T + T + j, epoch);
+        }
+      }
     }
     BA_TRACE(t, 5);   // published
   }
@@ -1118,12 +1396,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // everything this task reads except the x_i is long finished when it starts: wait for all of
     // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
-    if (tid == 0) {
-      while (ld_acquire(&g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7]) != epoch) __nanosleep(20);   // L_kk^{-1}
-      while (ld_acquire(&g.flags[(size_t)T * T + T + k]) != epoch) __nanosleep(20);      // y_k
-      for (int i = T - 1; i > k; --i)
-        while (ld_acquire(&g.flags[(size_t)i * T + k]) != epoch) __nanosleep(20);        // tiles (i, k)
-    }
+    wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0);   // L_kk^{-1}
+    wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0);                        // y_k
+    for (int i = T - 1; i > k; --i) wait_flag<DIST>(g, &g.flags[(size_t)i * T + k], epoch, s_t0);   // tiles (i, k)
     __syncthreads();
     {
       const double* LT = g.LinvT + (size_t)k * NB * NB;
@@ -1148,11 +1423,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // (8-byte stores are single-copy atomic; no fence on the producer, one round trip here,
       // no CTA barrier)
       double x0, x1;
+      unsigned int xspins = 0;
       for (;;) {
         x0 = ld_relaxed_f64(g.x + i * NB + lane);
         x1 = ld_relaxed_f64(g.x + i * NB + 32 + lane);
         const bool ok = __double_as_longlong(x0) != kNotYet && __double_as_longlong(x1) != kNotYet;
         if (__all_sync(0xffffffffu, ok)) break;
+        bool give_up = false;
+        if (lane == 0) give_up = spin_expired(g, xspins, s_t0);
+        if (__shfl_sync(0xffffffffu, (int)give_up, 0)) break;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) cs[q] += la[q] * x0 + lb[q] * x1;
@@ -1181,25 +1460,125 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       if (__double_as_longlong(xv) == kNotYet) xv = __longlong_as_double(0x7ff8000000000000LL);   // (cannot happen: keeps a NaN solve from hanging)
       st_relaxed_f64(g.x + k * NB + tid, xv);
     }
+    if (DIST && k == 0 && tid == 0) {   // a pivot that failed on the chain's rank fails the solve on every rank
+      if (*reinterpret_cast<volatile double*>(g.base[g.rank] + dl.status) != 0.0 && *g.status == 0.0) *g.status = 1.0;
+    }
     BA_TRACE(ntasks + bt, 5);
   }
 }
 
 // ------------------------------------------------------------------------------------------
+// Tile ownership of the distributed solve (deterministic, the same on every rank).  Rank 0 keeps
+// the chain tasks and the band 2 <= i - j <= band next to the diagonal: the critical path
+// C_j -> (j+2, j) -> C_{j+1} never crosses a link.  What is left of row i (tasks (i, j), j < i - band)
+// goes to ONE rank, so L_ij -> task (i, j+1) stays a local, progressive hand-over; rows are dealt
+// longest first to the least loaded rank (cost ~ one k step per finished column + the panel phase).
+std::vector<int> dist_task_list(int T, int world, int rank, int band) {
+  std::vector<double> load(world, 0.0);
+  std::vector<int> owner(T, 0);
+  auto cost = [](int i, int j) { return (i == j) ? 2.0 * (j > 0 ? j - 1 : 0) + 8.0 : (double)j + 2.0; };
+  for (int j = 0; j < T; ++j) load[0] += cost(j, j);
+  std::vector<std::pair<double, int>> rows;
+  for (int i = 0; i < T; ++i) {
+    double rc = 0.0;
+    for (int j = 0; j + 1 < i; ++j) {
+      if (i - j <= band) load[0] += cost(i, j);
+      else rc += cost(i, j);
+    }
+    rows.push_back(std::make_pair(-rc, i));
+  }
+  std::sort(rows.begin(), rows.end());
+  for (const auto& rw : rows) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[rw.second] = best;
+    load[best] += -rw.first;
+  }
+  std::vector<int> mine;
+  if (rank == 0) mine.push_back(0);   // C_0
+  for (int jc = 0; jc + 1 < T; ++jc) {
+    if (rank == 0) mine.push_back(((jc + 1) << 16) | (jc + 1));   // C_{jc+1}
+    for (int i = jc + 2; i < T; ++i) {
+      const int o = (i - jc <= band) ? 0 : owner[i];
+      if (o == rank) mine.push_back((i << 16) | jc);
+    }
+  }
+  return mine;
+}
+
+bool dist_solve_selected(const Context& c) {
+  return c.comm_world > 1 && c.comm_buf && c.dist_off != 0 && c.sys_state == kSysLocal && c.dist_min_tiles > 0 &&
+         c.ld / NB >= c.dist_min_tiles && c.ld / NB < 65536;
+}
+
+static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st) {
+  const int ld = c.ld, T = ld / NB;
+  const DistLayout dl = dist_layout(ld);
+  cudaError_t e;
+  if (!c.dist_tasks) {
+    const std::vector<int> mine = dist_task_list(T, c.comm_world, c.comm_rank, c.dist_band);
+    if ((e = cudaMalloc((void**)&c.dist_tasks, (mine.size() + 1) * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(c.dist_tasks, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // `mine` goes out of scope
+    c.dist_ntasks = (int)mine.size();
+  }
+  double* base = c.comm_buf + c.dist_off;
+  // this rank's contribution, dense: masked / padding parameters get their unit pivot from rank 0 only
+  expand_system_kernel<<<ld, 256, 0, st>>>(c.sys, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask, base + dl.contrib,
+                                           base + dl.contrib + (size_t)ld * ld, c.solve_tickets, &c.scalars->status, c.dC,
+                                           reinterpret_cast<unsigned int*>(base + dl.abort), base + dl.status,
+                                           c.comm_rank == 0 ? 1.0 : 0.0);
+  c.launches += 1;
+  if (!c.dist_attr_set) {
+    if ((e = cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSolveSmemBytes)) != cudaSuccess) return e;
+    c.dist_attr_set = true;
+  }
+  CholArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = base + dl.L;
+  g.rhs = g.A + (size_t)ld * ld;
+  g.x = c.dC;
+  g.LinvT = base + dl.LinvT;
+  g.flags = reinterpret_cast<unsigned int*>(base + dl.flags);
+  g.tickets = c.solve_tickets;
+  g.status = &c.scalars->status;
+  g.ld = ld; g.T = T;
+  g.epoch = ++c.dist_epoch;   // collective: every rank calls the distributed solve the same number of times
+  g.abort = reinterpret_cast<unsigned int*>(base + dl.abort);
+  g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
+  g.strict = 1;
+  g.world = c.comm_world; g.rank = c.comm_rank;
+  g.tasks = c.dist_tasks; g.ntasks = c.dist_ntasks;
+  for (int p = 0; p < kMaxPeers; ++p) g.base[p] = p < c.comm_world ? c.comm_peer[p] + c.dist_off : nullptr;
+#ifdef BA_SOLVE_TRACE
+  g.trace = c.solve_trace;
+#endif
+  int grid = c.num_sms;   // every rank runs the backward substitution: at least T tasks everywhere
+  if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
+  chol_dataflow_kernel<true><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
+  c.launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
+  if (dist_solve_selected(c)) return launch_solve_dist(c, have_mask, st);
   const int ld = c.ld, T = ld / NB;
   cudaError_t e;
   // sharded problems: factor the all-reduced copy the peers pushed (ba_comm.cu), not the local contribution
-  const double* packed = (c.sys_reduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
+  const double* packed = (c.sys_state == kSysReduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
   expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask,
-                                           c.Adense, c.Adense + (size_t)ld * ld, c.solve_tickets, &c.scalars->status, c.dC);
+                                           c.Adense, c.Adense + (size_t)ld * ld, c.solve_tickets, &c.scalars->status, c.dC,
+                                           c.solve_abort, nullptr, 1.0);
   c.launches += 1;
   if (!c.solve_attr_set) {
-    if ((e = cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSolveSmemBytes)) != cudaSuccess) return e;
     c.solve_attr_set = true;
   }
   CholArgs g;
+  memset(&g, 0, sizeof g);
   g.A = c.Adense;
   g.rhs = c.Adense + (size_t)ld * ld;
   g.x = c.dC;
@@ -1209,12 +1588,17 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   g.status = &c.scalars->status;
   g.ld = ld; g.T = T;
   g.epoch = ++c.solve_epoch;   // a fresh epoch per call: flags never need clearing
+  g.abort = c.solve_abort;
+  g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
+  g.strict = c.strict_flags;
+  g.world = 1; g.rank = 0;
 #ifdef BA_SOLVE_TRACE
   g.trace = c.solve_trace;
 #endif
   const int ntasks = 1 + T * (T - 1) / 2;
   int grid = ntasks < c.num_sms ? ntasks : c.num_sms;   // 1 CTA / SM (128 KB smem): all co-resident
-  chol_dataflow_kernel<<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
+  if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
+  chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
   c.launches += 1;
   return cudaGetLastError();
 }

@@ -195,7 +195,8 @@ class DeviceProblem(object):
         self.sys_len = int(self.lib.ba_system_size(scene.n_opt_cam))
         self.sys = torch.zeros(max(self.sys_len, 2), dtype=torch.float64, device=dev)
         h = ctypes.c_void_p()
-        rc = self.lib.ba_create(dev.index or 0, scene.n_cam, scene.n_pt, scene.n_obs, scene.n_opt_cam,
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        rc = self.lib.ba_create(dev_index, scene.n_cam, scene.n_pt, scene.n_obs, scene.n_opt_cam,
                                 scene.n_opt_pt, ctypes.byref(h))
         _lib.check(None, rc, "ba_create")
         self.h = h
@@ -212,6 +213,14 @@ class DeviceProblem(object):
         self._chk(self.lib.ba_scalars_ptr(h, ctypes.byref(sp)), "ba_scalars_ptr")
         self._scalars_ptr = sp.value
         self.peer_comm = False
+        self.dist_solve = False     # sharded + large reduced system: ba_solve is the distributed solve
+        import os
+        for env, opt in (("PYSFM_B200_SPIN_TIMEOUT_MS", _lib.BA_OPT_SPIN_TIMEOUT_MS),
+                         ("PYSFM_B200_STRICT_FLAGS", _lib.BA_OPT_STRICT_FLAGS),
+                         ("PYSFM_B200_DIST_SOLVE_MIN_TILES", _lib.BA_OPT_DIST_SOLVE_MIN_TILES),
+                         ("PYSFM_B200_DIST_BAND", _lib.BA_OPT_DIST_BAND)):
+            if os.environ.get(env):
+                self.set_option(opt, float(os.environ[env]))
 
     # -- plumbing --------------------------------------------------------------------------
     def _chk(self, rc, what):
@@ -224,6 +233,10 @@ class DeviceProblem(object):
         s, c = self.params[self.cur], self.params[1 - self.cur]
         self._chk(self.lib.ba_bind_state(self.h, _as_vp(s["R"]), _as_vp(s["t"]), _as_vp(s["x"])), "ba_bind_state")
         self._chk(self.lib.ba_bind_candidate(self.h, _as_vp(c["R"]), _as_vp(c["t"]), _as_vp(c["x"])), "ba_bind_candidate")
+
+    def set_option(self, option, value):
+        self._chk(self.lib.ba_set_option(self.h, int(option), float(value)), "ba_set_option")
+        self.dist_solve = bool(self.lib.ba_dist_solve_active(self.h))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -312,12 +325,14 @@ class DeviceProblem(object):
         self._chk(self.lib.ba_set_solution(self.h, a.ctypes.data_as(ctypes.c_void_p), self._stream()), "ba_set_solution")
 
     def upload_system(self, A, b):
-        """Overwrite the bound reduced system with a caller-supplied dense symmetric A and b."""
+        """Overwrite the bound reduced system with a caller-supplied dense symmetric A and b; the
+        next solve factors exactly this system on this rank (ba_upload_system)."""
         n = self.n_sys
         A = np.asarray(A, dtype=np.float64).reshape(n, n)
         host = np.zeros(max(self.sys_len, 2))
         host[:self.sys_len] = pack_system(A, b)
-        self.sys.copy_(self.torch.as_tensor(host))
+        self._chk(self.lib.ba_upload_system(self.h, host.ctypes.data_as(ctypes.c_void_p), self._stream()),
+                  "ba_upload_system")
 
     def copy_solution_to(self, out_dC, out_dP):
         """D2H of the camera solution and the point update into caller (pinned) torch tensors."""
@@ -365,7 +380,8 @@ class DeviceProblem(object):
         self._chk(self.lib.ba_trial_host_packed(self.h, None if in_flat is None else self._host_ptr(in_flat, n_in),
                                                 float(damping), float(rcond), mp, self._host_ptr(out_flat, n_out),
                                                 self._stream()), "ba_trial_host_packed")
-        status = _lib.BA_ERR_ILLCONDITIONED if float(out_flat[2]) != 0.0 else _lib.BA_OK
+        st = float(out_flat[2])
+        status = _lib.BA_ERR_TIMEOUT if st == 2.0 else _lib.BA_ERR_ILLCONDITIONED if st != 0.0 else _lib.BA_OK
         return (float(out_flat[0]), float(out_flat[1]), status, out_flat[4:4 + self.n_sys],
                 out_flat[4 + self.ld:])
 
@@ -403,6 +419,7 @@ class DeviceProblem(object):
         self._sys_keepalive = w
         self.sys = torch.as_tensor(w, device=self.device)
         self.peer_comm = True
+        self.dist_solve = bool(self.lib.ba_dist_solve_active(self.h))
         return True
 
     def disable_peer_comm(self):
@@ -411,6 +428,7 @@ class DeviceProblem(object):
             self.sys = self._torch_sys
         self._chk(self.lib.ba_bind_system(self.h, _as_vp(self.sys)), "ba_bind_system")
         self.peer_comm = False
+        self.dist_solve = False
 
     def allreduce_system(self):
         self._chk(self.lib.ba_allreduce_system(self.h, self._stream()), "ba_allreduce_system")
@@ -447,7 +465,10 @@ class DeviceProblem(object):
 
     def system(self):
         """(A, b): A = dense symmetric (n_sys, n_sys) rebuilt from the packed upper blocks."""
-        return unpack_system(self.sys.cpu().numpy()[:self.sys_len], self.scene.n_opt_cam)
+        host = np.empty(max(self.sys_len, 1), dtype=np.float64)
+        self._chk(self.lib.ba_get_system(self.h, host.ctypes.data_as(ctypes.c_void_p), self.sys_len, self._stream()),
+                  "ba_get_system")
+        return unpack_system(host[:self.sys_len], self.scene.n_opt_cam)
 
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))

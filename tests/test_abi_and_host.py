@@ -75,7 +75,10 @@ def test_hot_kernels_use_the_fp64_tensor_pipe_and_the_tma_path():
     assert count("chol_dataflow_kernel", "LDGSTS") >= 4
     assert count("linearize_eliminate_kernel", "UBLKRED") >= 4
     # nothing in the product path may fall back to a local-memory stack of any size that matters
-    assert count("chol_dataflow_kernel", "STL") <= 8
+    # (ILb0E = the single-GPU solver, ILb1E = the distributed variant with its peer pushes)
+    assert count("chol_dataflow_kernelILb0E", "STL") <= 8
+    assert count("chol_dataflow_kernelILb1E", "STL") <= 32
+    assert count("chol_dataflow_kernelILb1E", "UBLKCP") >= 2
 
 
 def test_no_cpu_fallback_without_cuda():
