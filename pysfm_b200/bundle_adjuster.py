@@ -123,6 +123,12 @@ class BundleAdjuster(object):
                 self._world, self._rank = dist.get_world_size(), dist.get_rank()
         self._packed_full = packed
         self._packed = packed.shard(self._rank, self._world)
+        if self._world > 1:
+            # every rank must own at least one point, and all ranks must find out together (a rank
+            # that failed alone would leave the others hanging in the next collective)
+            sizes = self._gather_objects(self._packed.n_pt)
+            assert min(sizes) >= 1, 'cannot shard %d tracks over %d ranks: some rank would own none (%s)' % (
+                packed.n_pt, self._world, sizes)
         self._problem = _scene.DeviceProblem(self._packed, self._device)
         self._scalars_t = self._problem.scalars_tensor() if self._world > 1 else None
         if self._world > 1 and self._peer_comm_wanted():
@@ -159,12 +165,15 @@ class BundleAdjuster(object):
         bundle.reconstruction[self.track_ids] = x
         return bundle
 
-    def _gather_points(self, x_local):
-        import torch
+    def _gather_objects(self, obj):
         import torch.distributed as dist
         parts = [None] * self._world
-        dist.all_gather_object(parts, np.asarray(x_local))
-        return np.concatenate(parts, axis=0)
+        dist.all_gather_object(parts, obj)
+        return parts
+
+    def _gather_points(self, x_local):
+        """Rows of every rank's shard, concatenated in rank (= point) order."""
+        return np.concatenate(self._gather_objects(np.asarray(x_local)), axis=0)
 
     # ------------------------------------------------------------------------------------------
     # collectives (only when points are sharded)
@@ -308,6 +317,14 @@ class BundleAdjuster(object):
         self.bCs = p.get_array(_lib.BA_ARR_BC, (sc.n_cam, 6))
         self.bPs = p.get_array(_lib.BA_ARR_BP, (sc.n_pt, 3))
         self.HCP_blocks = p.get_array(_lib.BA_ARR_HCP, (sc.n_obs, 6, 3))
+        if self._world > 1:
+            # camera blocks are sums over the ranks' points; point and observation blocks concatenate
+            self.HCCs = np.sum(self._gather_objects(self.HCCs), axis=0)
+            self.bCs = np.sum(self._gather_objects(self.bCs), axis=0)
+            self.HPPs = self._gather_points(self.HPPs)
+            self.bPs = self._gather_points(self.bPs)
+            self.HCP_blocks = self._gather_points(self.HCP_blocks)
+        sc = self._packed_full
         self.HPP_invs = np.empty((sc.n_pt, 3, 3))
         self._damp_factor = 1.0
         self._blocks.pop('HCPs', None)
@@ -317,7 +334,7 @@ class BundleAdjuster(object):
         """Dense (nc, nt, 6, 3) cross blocks like the reference's attribute (:107); built on
         demand from the per-observation blocks."""
         if 'HCPs' not in self._blocks:
-            sc = self._packed
+            sc = self._packed_full
             nbytes = sc.n_cam * sc.n_pt * 18 * 8
             assert nbytes <= (1 << 30), \
                 'dense HCPs would take %.1f GB; use HCP_blocks (one 6x3 block per observation)' % (nbytes / 1e9)
@@ -343,6 +360,8 @@ class BundleAdjuster(object):
         p.linearize_eliminate(self._damp_factor - 1.0, self._rcond(), _lib.BA_WANT_SCHUR)
         self._allreduce_system()
         self.HPP_invs = p.get_array(_lib.BA_ARR_HPP_INV, (sc.n_pt, 3, 3))
+        if self._world > 1:
+            self.HPP_invs = self._gather_points(self.HPP_invs)
         A, b = p.system()
         nc = sc.n_opt_cam
         S = A.reshape(nc, 6, nc, 6).transpose(0, 2, 1, 3).copy()
@@ -369,7 +388,8 @@ class BundleAdjuster(object):
         p.set_solution(np.asarray(dC, dtype=np.float64).reshape(-1, 6))
         p.backsub_retract_cost()
         dP_all = p.get_array(_lib.BA_ARR_DP, (self._packed.n_pt, 3))
-        return dP_all[self._packed.optim_track_indices]
+        dP = dP_all[self._packed.optim_track_indices]
+        return self._gather_points(dP) if self._world > 1 else dP
 
     # ------------------------------------------------------------------------------------------
     def update_motion(self, delta, bundle):
@@ -386,8 +406,13 @@ class BundleAdjuster(object):
         """x <- x + delta on the optimised tracks (:340-343)."""
         assert np.shape(delta) == (len(self.optim_track_ids), 3)
         self._push(bundle)
-        self._problem.retract(delta_cam=None, delta_pt=delta)
+        lo = self._packed.shard_opt_lo      # sharded: this rank retracts its own rows of delta
+        local = np.asarray(delta, dtype=np.float64)[lo:lo + self._packed.n_opt_pt]
+        self._problem.retract(delta_cam=None, delta_pt=local)
         _, _, x = self._problem.download("candidate")
+        x = x[self._packed.optim_track_indices]
+        if self._world > 1:
+            x = self._gather_points(x)
         bundle.reconstruction = np.array(bundle.reconstruction, dtype=np.float64)
         ids = np.asarray(self.optim_track_ids, dtype=np.int64)
-        bundle.reconstruction[ids] = x[self._packed.optim_track_indices]
+        bundle.reconstruction[ids] = x

@@ -1320,7 +1320,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       BA_TRACE(t, 4);   // sweep done
       const bool bad = s_bad != 0;
       if (bad) {   // leave an identity behind so that dependants stay finite
-        if (tid == 0) *g.status = 1.0;
+        if (tid == 0 && ld_relaxed_sys(g.abort) == 0u) *g.status = 1.0;   // (an aborted launch computes garbage: it stays "timed out")
         for (int e = tid; e < NB * NB; e += kSolveThreads) {
           const double v = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
           LTs[(e >> 6) * LDT + (e & 63)] = v;

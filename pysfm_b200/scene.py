@@ -18,7 +18,8 @@ class PackedScene(object):
     """Host-side SoA image of the selected sub-problem."""
     __slots__ = ("camera_ids", "track_ids", "optim_camera_indices", "optim_track_indices",
                  "K", "model_kind", "model_params", "cam_R", "cam_t", "pts",
-                 "pt_ptr", "obs_cam", "obs_uv", "obs_track", "cam_slot", "pt_slot")
+                 "pt_ptr", "obs_cam", "obs_uv", "obs_track", "cam_slot", "pt_slot",
+                 "shard_lo", "shard_obs_lo", "shard_opt_lo")   # position of a shard inside the whole selection
 
     @property
     def n_cam(self):
@@ -44,6 +45,7 @@ class PackedScene(object):
         """Contiguous point range for `rank`, balanced by observation count (cameras, K and
         the sensor model are replicated).  Returns a new PackedScene sharing camera arrays."""
         if world_size == 1:
+            self.shard_lo = self.shard_obs_lo = self.shard_opt_lo = 0
             return self
         nobs = self.n_obs
         targets = [(nobs * r) // world_size for r in range(world_size + 1)]
@@ -68,6 +70,8 @@ class PackedScene(object):
         ps = np.full(hi - lo, -1, dtype=np.int32)
         ps[out.optim_track_indices] = np.arange(len(out.optim_track_indices), dtype=np.int32)
         out.pt_slot = ps
+        out.shard_lo, out.shard_obs_lo = lo, o0
+        out.shard_opt_lo = int(np.count_nonzero(self.pt_slot[:lo] >= 0))   # updated tracks that precede the shard
         return out
 
 
@@ -123,6 +127,7 @@ def pack_scene(bundle, camera_ids, track_ids, optim_camera_indices, optim_track_
     s.obs_cam = o_cam.astype(np.int32)
     s.obs_track = o_trk.astype(np.int32)
     s.obs_uv = np.ascontiguousarray(o_uv, dtype=np.float64)
+    s.shard_lo = s.shard_obs_lo = s.shard_opt_lo = 0
     return s
 
 
