@@ -364,7 +364,7 @@ def run_c4(args, dev, world, rank):
                "final": {"cost": cost, "cand_cost": cand, "solve_status": status},
                "parity": par, "setup_s": setup_s, "oracle_cpu_s_per_step": float(g["seconds"])}
     h.barrier()
-    del h
+    h.ba.close()
     return out
 
 
@@ -460,6 +460,7 @@ def run_ours(args):
     n_pt_local, n_obs_local, n_cam = sc.n_pt, sc.n_obs, sc.n_cam
     pairs = float(np.sum((np.diff(sc.pt_ptr).astype(np.float64)) * (np.diff(sc.pt_ptr) + 1) / 2))
     H.barrier()
+    ba.close()
     del H, ba, prob
 
     # ---- BASELINE config 4 (strong scaling), every N, unless --no-c4 -----------------------------

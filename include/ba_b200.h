@@ -204,6 +204,10 @@ int ba_scalars_ptr(ba_handle h, double** scalars_dev);
  * All ranks must issue the same sequence of these two calls. */
 int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_out64);
 int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all);
+/* Unmaps the peers' buffers.  Tear-down is collective: every rank disconnects, the host side
+ * synchronises the ranks, and only then may a rank destroy its handle (which frees the buffer its
+ * peers had mapped). */
+int ba_comm_disconnect(ba_handle h);
 int ba_comm_system_ptr(ba_handle h, double** sys_dev);
 int ba_allreduce_system(ba_handle h, void* stream);
 int ba_allreduce_costs(ba_handle h, void* stream);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ba_scalars_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "ba_comm_create": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "ba_comm_connect": (ctypes.c_int, [_vp, _vp]),
+    "ba_comm_disconnect": (ctypes.c_int, [_vp]),
     "ba_comm_system_ptr": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
     "ba_allreduce_system": (ctypes.c_int, [_vp, _vp]),
     "ba_allreduce_costs": (ctypes.c_int, [_vp, _vp]),

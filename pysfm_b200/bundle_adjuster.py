@@ -112,8 +112,7 @@ class BundleAdjuster(object):
         assert len(self.optim_track_ids) == len(self.optim_track_indices)
         assert len(self.optim_camera_ids) == len(self.optim_camera_indices)
 
-        if self._problem is not None:
-            self._problem.close()
+        self.close()
         packed = _scene.pack_scene(bundle, self.camera_ids, self.track_ids,
                                    self.optim_camera_indices, self.optim_track_indices)
         self._world, self._rank = 1, 0
@@ -144,6 +143,20 @@ class BundleAdjuster(object):
         self._blocks = {}
         self._say('Configured a bundle adjuster for %d cameras, %d tracks' %
                   (len(self.camera_ids), len(self.track_ids)))
+
+    def close(self):
+        """Release the device problem.  Sharded over peer memory this is collective: every rank
+        unmaps its peers' buffers, the ranks synchronise, then each frees its own."""
+        p = self._problem
+        if p is None:
+            return
+        if getattr(self, "_world", 1) > 1 and p.peer_comm:
+            import torch.distributed as dist
+            p.disconnect_peers()
+            if dist.is_initialized():
+                dist.barrier()
+        p.close()
+        self._problem = None
 
     # ------------------------------------------------------------------------------------------
     # device <-> host state

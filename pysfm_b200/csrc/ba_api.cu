@@ -131,6 +131,7 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->io_out, (size_t)4 + c->ld + (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->Adense, (size_t)c->ld * c->ld + c->ld) == cudaSuccess &&
             dev_alloc(&c->LinvT, T * ba::kSolveTile * ba::kSolveTile) == cudaSuccess &&
+            dev_alloc(&c->Wpart, T * (ba::kSolveTile * ba::kSolveTile + ba::kSolveTile)) == cudaSuccess &&
             dev_alloc(&c->solve_flags, ba::solve_flag_count((int)T)) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->solve_abort, (size_t)2) == cudaSuccess &&
@@ -158,7 +159,7 @@ int ba_destroy(ba_handle h) {
   DeviceGuard guard__(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->Adense, h->LinvT, h->solve_flags, h->solve_tickets, h->solve_abort, h->dist_tasks};
+                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->dist_tasks};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
@@ -204,6 +205,18 @@ int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all) {
     BA_CUDA(h, cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
     h->comm_peer[p] = static_cast<double*>(ptr);
   }
+  return BA_OK;
+}
+
+int ba_comm_disconnect(ba_handle h) {
+  if (!h) return BA_ERR_BAD_ARGUMENT;
+  BA_ON_DEVICE(h);
+  BA_CUDA(h, cudaDeviceSynchronize());
+  for (int p = 0; p < ba::kMaxPeers; ++p)
+    if (h->comm_peer[p] && p != h->comm_rank) {
+      cudaIpcCloseMemHandle(h->comm_peer[p]);
+      h->comm_peer[p] = nullptr;
+    }
   return BA_OK;
 }
 

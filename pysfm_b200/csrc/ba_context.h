@@ -25,10 +25,11 @@ inline size_t comm_doubles(size_t sys_len) { return 2 * comm_pad(sys_len) + 4 * 
 //   contrib [ld*ld + ld]   this rank's dense lower-triangular contribution + its rhs (expand_system_kernel)
 //   L       [ld*ld + ld]   the factor, replicated: every tile is computed by ONE rank and pushed to all; rhs -> y
 //   LinvT   [T][64*64]     transposed inverses of the diagonal tiles (pushed row block by row block)
+//   wpart   [T][64*64+64]  partial diagonal tiles / forward-substitution sums (diagonal-update tasks -> chain tasks)
 //   flags   [solve_flag_count(T)] u32, same layout as the single-GPU solver's, written by the tile owners
 //   bar     [kMaxPeers] u32  start barrier (epoch valued)  | abort u32 | pad | status f64
 struct DistLayout {
-  size_t contrib, L, LinvT, flags, bar, abort, status, total;
+  size_t contrib, L, LinvT, wpart, flags, bar, abort, status, total;
 };
 __host__ __device__ inline DistLayout dist_layout(int ld) {
   const size_t T = (size_t)ld / kSolveTile;
@@ -38,7 +39,8 @@ __host__ __device__ inline DistLayout dist_layout(int ld) {
   d.contrib = 0;
   d.L = d.contrib + ((dense + 1) & ~(size_t)1);
   d.LinvT = d.L + ((dense + 1) & ~(size_t)1);
-  d.flags = d.LinvT + T * kSolveTile * kSolveTile;
+  d.wpart = d.LinvT + T * kSolveTile * kSolveTile;     // D_j -> C_j hand-over, local to the chain's rank
+  d.flags = d.wpart + T * (kSolveTile * kSolveTile + kSolveTile);
   d.bar = d.flags + (((nflags + 3) / 2) & ~(size_t)1);
   d.abort = d.bar + kMaxPeers / 2;
   d.status = d.abort + 2;
@@ -98,6 +100,7 @@ struct Context {
   double* dC = nullptr;     // [ld]        reduced solution (inside io_out)
   double* Adense = nullptr; // [ld*ld + ld] dense lower-triangular copy + rhs, factored in place
   double* LinvT = nullptr;  // [ld/64][64*64] transposed inverses of the diagonal Cholesky tiles
+  double* Wpart = nullptr;  // [ld/64][64*64 + 64] partial diagonal tiles + forward-substitution sums (D_j -> C_j)
   unsigned int* solve_flags = nullptr;    // [solve_flag_count(T)] tile / y_k / Linv row-block / L column-block ready flags (epoch valued)
   unsigned int* solve_tickets = nullptr;  // [2] task tickets of the dataflow solver
   unsigned long long* solve_trace = nullptr;  // debug timeline (BA_SOLVE_TRACE builds only)

@@ -54,6 +54,7 @@ constexpr int NBP = NB + 1;        // padded row of the diagonal-tile work array
 constexpr int kSolveThreads = 256;
 // A quiet NaN with a payload no arithmetic produces: marks entries of x that are not computed yet.
 constexpr long long kNotYet = 0x7ff8dead0000beefLL;
+constexpr int kDiagTask = 0x40000000;   // task code of the distributed solve: diagonal-update task D_j (low 16 bits = j)
 
 // ------------------------------------------------------------------------------------------
 // packed block index of (a, b), a <= b < nc:  rows of the upper block triangle back to back
@@ -237,13 +238,27 @@ __device__ int g_dbg_producer = 36, g_dbg_consumer = 52;
 #define BA_TRACE_SET(rec, slot, v) do { } while (0)
 #endif
 
+// Optional wait-time profile (tools/microbench/*solve_bench.cu define BA_SOLVE_PROF): nanoseconds
+// the polling thread of each wait site spent waiting, summed over the CTAs of a launch.
+#ifdef BA_SOLVE_PROF
+__device__ unsigned long long g_prof[8][16];   // [rank][site]
+#define BA_PROF_T0() const unsigned long long pt0__ = global_ns()
+#define BA_PROF_ADD(site) atomicAdd(&g_prof[g.rank & 7][(site)], global_ns() - pt0__)
+#else
+#define BA_PROF_T0() do { } while (0)
+#define BA_PROF_ADD(site) do { } while (0)
+#endif
+enum { kProfTask = 0, kProfWaitK = 1, kProfLast = 2, kProfPanel = 3, kProfDiagFlag = 4, kProfPush = 5, kProfContrib = 6,
+       kProfYflag = 7, kProfBackward = 8, kProfBarrier = 9, kProfKernel = 10, kProfChainTask = 11, kProfDiagTask = 12 };
+
 struct CholArgs {
   BA_TRACE_DECL
   double* __restrict__ A;         // [ld*ld] dense lower, column-major; overwritten by L
   double* __restrict__ rhs;       // [ld] b -> y (forward substitution)
   double* __restrict__ x;         // [ld] solution
   double* __restrict__ LinvT;     // [T][NB*NB]  LinvT[m*NB + c] = (L_jj^{-1})[c][m]
-  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + k] x_k ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready ; [T*T + 10T + 8(iT+j) + b] columns 8b.. of L_ij ready
+  double* __restrict__ Wpart;     // [T][NB*NB + NB]  D_j -> C_j: A_jj - sum_{k<j-2} L_jk L_jk^T ([col][row], lower) | sum_{k<j-2} L_jk y_k
+  unsigned int* __restrict__ flags;   // [T*T] tile (i,j) ready == epoch ; [T*T + j] D_j's partial diagonal tile ready ; [T*T + T + k] y_k ready ; [T*T + 2T + 8k + b] rows 8b.. of Linv_kk ready ; [T*T + 10T + 8(iT+j) + b] columns 8b.. of L_ij ready
   unsigned int* __restrict__ tickets; // [0] tile tasks, [1] back-substitution tasks
   double* __restrict__ status;    // set to 1 on a non-positive pivot, 2 when a spin-wait ran past the deadline
   int ld, T;
@@ -284,13 +299,18 @@ __device__ __forceinline__ bool spin_expired(const CholArgs& g, unsigned int& sp
 
 // Block-wide wait until *f == epoch (thread 0 spins with acquire loads).
 template <bool SYS>
-__device__ __forceinline__ void wait_flag(const CholArgs& g, const unsigned int* f, unsigned int epoch, const unsigned long long& t0) {
+__device__ __forceinline__ void wait_flag(const CholArgs& g, const unsigned int* f, unsigned int epoch, const unsigned long long& t0,
+                                          int site = kProfWaitK) {
   if (threadIdx.x == 0) {
     unsigned int spins = 0;
+    if (ldf_acquire<SYS>(f) == epoch) return;
+    BA_PROF_T0();
     while (ldf_acquire<SYS>(f) != epoch) {
       if (spin_expired(g, spins, t0)) break;
       __nanosleep(20);
     }
+    BA_PROF_ADD(site);
+    (void)site;
   }
 }
 
@@ -463,7 +483,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   const int R0 = 32 * (wid & 1), C0 = 16 * (wid >> 1);
   const int T = g.T;
   const size_t ld = (size_t)g.ld;
-  const int ntasks = DIST ? g.ntasks : 1 + T * (T - 1) / 2;   // chain task C_0, then per column one chain + the panels below
+  const int ntasks = DIST ? g.ntasks : 1 + (T - 1) * (T + 2) / 2;   // C_0, then per column: diagonal-update task, chain task, the panels below
   const unsigned int epoch = g.epoch;
   const DistLayout dl = dist_layout(g.ld);
   if (tid == 0) s_t0 = global_ns();
@@ -478,10 +498,12 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     if (tid < g.world) {
       const unsigned int* mine = reinterpret_cast<const unsigned int*>(g.base[g.rank] + dl.bar) + tid;
       unsigned int spins = 0;
+      BA_PROF_T0();
       while (ld_acquire_sys(mine) != epoch) {
         if (spin_expired(g, spins, s_t0)) break;
         __nanosleep(100);
       }
+      if (tid == 0) BA_PROF_ADD(kProfBarrier);
     }
     __syncthreads();
   }
@@ -508,43 +530,50 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     const int t = s_task;
     if (t >= ntasks) break;
     bool chain = true;
-    int j = 0;          // chain: diagonal tile index;  panel: column
-    int pi = 0, pj = 0; // the panel tile (pi, pj) of this task (chain: (j, j - 1))
+    bool diag = false;  // diagonal-update task D_j
+    int j = 0;          // chain / diag: diagonal tile index;  panel: column
+    int pi = 0, pj = 0; // the panel tile (pi, pj) of this task (chain and diag: (j, j - 1))
     if (DIST) {
       const int code = g.tasks[t];
-      pi = code >> 16;
+      diag = (code & kDiagTask) != 0;
+      pi = (code >> 16) & 0x3fff;
       pj = code & 0xffff;
-      chain = (pi == pj);
+      chain = !diag && (pi == pj);
       j = pj;
-      if (chain && j > 0) pj = j - 1;
+      if (diag) pi = j;
+      if ((chain || diag) && j > 0) pj = j - 1;
     } else if (t > 0) {
-      // column-major enumeration over columns 0 .. T-2, column jc holding T-1-jc tasks
+      // column-major enumeration over columns 0 .. T-2, column jc holding T - jc tasks:
+      // D_{jc+1}, C_{jc+1}, (jc+2, jc), ..., (T-1, jc)
       const int tt = t - 1;
-      const double Tf = (double)Tm + 0.5;
+      const double Tf = (double)T + 0.5;
       int jc = (int)(Tf - sqrt(Tf * Tf - 2.0 * (double)tt));
       if (jc < 0) jc = 0;
       if (jc > Tm - 1) jc = Tm - 1;
-      while (jc > 0 && (size_t)jc * Tm - (size_t)jc * (jc - 1) / 2 > (size_t)tt) --jc;
-      while ((size_t)(jc + 1) * Tm - (size_t)(jc + 1) * jc / 2 <= (size_t)tt) ++jc;
-      const int rem = tt - (int)((size_t)jc * Tm - (size_t)jc * (jc - 1) / 2);
-      chain = (rem == 0);
-      j = chain ? jc + 1 : jc;
-      pi = jc + 1 + rem;
+      while (jc > 0 && (size_t)jc * T - (size_t)jc * (jc - 1) / 2 > (size_t)tt) --jc;
+      while (jc < Tm - 1 && (size_t)(jc + 1) * T - (size_t)(jc + 1) * jc / 2 <= (size_t)tt) ++jc;
+      const int rem = tt - (int)((size_t)jc * T - (size_t)jc * (jc - 1) / 2);
+      diag = (rem == 0);
+      chain = (rem == 1);
+      j = (diag || chain) ? jc + 1 : jc;
+      pi = (diag || chain) ? jc + 1 : jc + rem;
       pj = jc;
     }
-    const bool has_panel = DIST ? !(chain && j == 0) : t > 0;
-    BA_TRACE_SET(t, 0, ((unsigned long long)(chain ? j : pi) << 32) | (unsigned)(chain ? j : pj));
+    const bool has_panel = !diag && !(chain && j == 0);
+    BA_TRACE_SET(t, 0, ((unsigned long long)((chain || diag) ? j : pi) << 32) | (unsigned)(chain ? j : diag ? (0x8000 | j) : pj));
     BA_TRACE_SET(t, 1, (unsigned long long)blockIdx.x);
     BA_TRACE(t, 2);   // task grabbed
+    BA_PROF_T0();
 
     // ---- original tiles first: their latency hides behind the k loop --------------------------
     const int r = row_block_of_warp(wid);   // row block owned in the diagonal tile
     Frag acc;            // panel tile  A_{pi,pj} - sum_k L_{pi,k} L_{pj,k}^T   (warp tile R0, C0)
     RowTiles W;          // diagonal tile A_jj - sum_k L_jk L_jk^T, lower triangle, row-block owned
     acc.zero();
-    // DIST: the original tile is the sum of the ranks' contributions.  Peer p's share of the panel
-    // tile is fetched at step p of the k loop and added after that step's products (fixed order:
-    // the result does not depend on timing); what the k loop is too short for follows after it.
+    // DIST: the original tile is the sum of the ranks' contributions, fetched from the peers' dense
+    // copies right here, two peers (round trips) in flight at a time, added in rank order.  (Riding
+    // on the first steps of the k loop instead hid the latency but kept 32 more registers live
+    // across the tile products: spills in the loop every task spends its life in.)
     const size_t tile_off = (size_t)(pj * NB) * ld + (size_t)pi * NB;
     auto contrib_load = [&](int p, Frag& c) {
       const double* Ap = g.base[p] + dl.contrib + tile_off;
@@ -566,6 +595,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll
           for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += c.v[mi][ni][e];
     };
+    if (DIST && has_panel) {
+      BA_PROF_T0();
+      for (int p = 0; p < g.world; p += 2) {
+        Frag c0, c1;
+        contrib_load(p, c0);
+        if (p + 1 < g.world) contrib_load(p + 1, c1);
+        contrib_add(c0);
+        if (p + 1 < g.world) contrib_add(c1);
+      }
+      if (tid == 0) BA_PROF_ADD(kProfContrib);
+    }
     if (!DIST && has_panel) {
       const double* Ap = g.A + (size_t)(pj * NB) * ld + (size_t)pi * NB;
 #pragma unroll
@@ -581,7 +621,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     double bacc = 0.0, rhs_j = 0.0;   // tid < NB: sum_k (L_jk y_k)[tid], b_j
 #pragma unroll
     for (int c = 0; c < 8; ++c) W.t[c][0] = W.t[c][1] = 0.0;
-    if (!DIST && chain) {
+    // The diagonal tile A_jj belongs to the diagonal-update task D_j (C_0 has none and loads its own);
+    // the chain task starts from W = 0, takes the updates of the last two columns itself and adds
+    // D_j's partial tile before its sweep.
+    const bool loadW = diag || (chain && j == 0);
+    if (!DIST && loadW) {
       const double* Ajj = g.A + (size_t)(j * NB) * ld + (size_t)j * NB;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -591,11 +635,12 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           const int hi = row > col ? row : col, lo = row > col ? col : row;
           if (c <= r) W.t[c][e] = __ldcg(Ajj + (size_t)lo * ld + hi);
         }
-      if (tid < NB) rhs_j = __ldcg(g.rhs + j * NB + tid);
     }
-    if (DIST && chain) {
-      // diagonal tile and right-hand side: summed here, in rank order.  A chain task is grabbed
-      // well before its last operand exists, so these round trips are off the critical path.
+    if (!DIST && chain && tid < NB) rhs_j = __ldcg(g.rhs + j * NB + tid);
+    if (DIST && (loadW || chain)) {
+      // diagonal tile (D_j / C_0) and right-hand side (chain): summed here, in rank order.  Both
+      // kinds of task are grabbed well before their last operand exists, so these round trips are
+      // off the critical path.
       for (int p = 0; p < g.world; ++p) {
         const double* Ajj = g.base[p] + dl.contrib + (size_t)(j * NB) * ld + (size_t)j * NB;
         double w[8][2];
@@ -605,9 +650,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           for (int e = 0; e < 2; ++e) {
             const int row = 8 * r + gq, col = 8 * c + 2 * t4 + e;
             const int hi = row > col ? row : col, lo = row > col ? col : row;
-            w[c][e] = (c <= r) ? ld_peer_f64(Ajj + (size_t)lo * ld + hi) : 0.0;
+            w[c][e] = (loadW && c <= r) ? ld_peer_f64(Ajj + (size_t)lo * ld + hi) : 0.0;
           }
-        const double rb = (tid < NB) ? ld_peer_f64(g.base[p] + dl.contrib + ld * ld + j * NB + tid) : 0.0;
+        const double rb = (chain && tid < NB) ? ld_peer_f64(g.base[p] + dl.contrib + ld * ld + j * NB + tid) : 0.0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) { W.t[c][0] += w[c][0]; W.t[c][1] += w[c][1]; }
         rhs_j += rb;
@@ -615,16 +660,21 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     }
 
     // ---- k loop over the finished columns k < pj:  P = L_{pi,k}, Q = L_{pj,k} ------------------
+    // Steps k < kfull take complete tiles.  A panel or chain task forms  acc -= L_{pi,k} L_{pj,k}^T;
+    // the diagonal-update task D_j  W -= L_jk L_jk^T  and the forward-substitution sum  L_jk y_k
+    // (one operand tile per step).  The chain task C_j used to do all three: its k loop then took
+    // 1.7x a panel task's and every panel task of column j idled that much behind it (the more
+    // ranks share a column, the more columns the chain fell behind).
     auto issue = [&](int k) {
       double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       stage_tile(P, g.A + (size_t)(k * NB) * ld + (size_t)pi * NB, ld);
-      stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)pj * NB, ld);
+      if (!diag) stage_tile(P + kTileDoubles, g.A + (size_t)(k * NB) * ld + (size_t)pj * NB, ld);
       cp_async_commit();
     };
     auto wait_k = [&](int k) {
       wait_flag<DIST>(g, &g.flags[(size_t)pi * T + k], epoch, s_t0);
-      wait_flag<DIST>(g, &g.flags[(size_t)pj * T + k], epoch, s_t0);
-      if (chain) wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
+      if (!diag) wait_flag<DIST>(g, &g.flags[(size_t)pj * T + k], epoch, s_t0);
+      if (diag) wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
     };
     // The tiles of step k+1 are prefetched while step k computes ONLY if they are already
     // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
@@ -654,15 +704,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             bool ok = false;
             if (lane < 8 && kk < kfull) {
               const unsigned int f0 = ldf_relaxed<DIST>(&g.flags[(size_t)pi * T + kk]);
-              const unsigned int f1 = ldf_relaxed<DIST>(&g.flags[(size_t)pj * T + kk]);
-              const unsigned int f2 = chain ? ldf_relaxed<DIST>(&yflag[kk]) : epoch;
+              const unsigned int f1 = diag ? epoch : ldf_relaxed<DIST>(&g.flags[(size_t)pj * T + kk]);
+              const unsigned int f2 = diag ? ldf_relaxed<DIST>(&yflag[kk]) : epoch;
               ok = f0 == epoch && f1 == epoch && f2 == epoch;
             }
             const unsigned int mask = __ballot_sync(0xffffffffu, ok) & 0xffu;
             if (lane == 0) {
               const unsigned int m = ~mask & 0xffu;
               const int n = m ? __ffs(m) - 1 : 8;      // consecutive ready steps from k + 1
-              if (n > 0) { if (DIST) __threadfence_system(); else __threadfence(); }   // acquire for what the relaxed loads saw
+              if (n > 0) { if (DIST && g.strict) __threadfence_system(); else __threadfence(); }   // acquire for what the relaxed loads saw
               s_task = k + n;
             }
           }
@@ -679,15 +729,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       } else {
         cp_async_wait<0>();
       }
-      if (chain && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
-      Frag ctmp;
-      const bool cadd = DIST && k < g.world;   // CTA-uniform
-      if (cadd) contrib_load(k, ctmp);
+      if (diag && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
       __syncthreads();
       const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
-      tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
-      if (cadd) contrib_add(ctmp);
-      if (chain) {
+      if (!diag) tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
+      if (diag) {
         diag_rows_dmma(W, P, r, lane);
         if (tid < NB) {
           double s = 0.0;
@@ -698,13 +744,24 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
       __syncthreads();
     }
-    int cnext = 0;   // DIST: contributions of peers [0, cnext) are in acc
-    if (DIST) cnext = kfull < g.world ? kfull : g.world;
+    if (diag) {
+      // D_j is done: partial diagonal tile (lower triangle, [col][row]) and partial sum to the chain task
+      double* Wp = g.Wpart + (size_t)j * (NB * NB + NB);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (c <= r) Wp[(8 * c + 2 * t4 + e) * NB + 8 * r + gq] = W.t[c][e];
+      if (tid < NB) Wp[NB * NB + tid] = bacc;
+      __syncthreads();
+      if (tid == 0) st_release(&g.flags[(size_t)T * T + j], epoch);
+      BA_TRACE(t, 3);
+      BA_TRACE(t, 5);
+      if (tid == 0) BA_PROF_ADD(kProfDiagTask);
+      continue;
+    }
     if (pj > 0) {
       const int k = pj - 1;
-      Frag clast;
-      const bool cl = DIST && cnext < g.world;   // one more peer rides on the last step
-      if (cl) contrib_load(cnext, clast);
       double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       double* Q = P + kTileDoubles;
       const double* gP = g.A + (size_t)(k * NB) * ld + (size_t)pi * NB;
@@ -722,6 +779,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       while (ca < 8 || cw < 8) {
         if (tid == 0) {
           unsigned int spins = 0;
+          BA_PROF_T0();
           for (;;) {
             unsigned int f[8], h[8];
 #pragma unroll
@@ -742,10 +800,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             const int eA = eP < eQ ? eP : eQ;
             const bool yr = !gemv_done && fy == epoch && eP == 8;
             if (eA > ca || eP > cw || yr) {
-              // acquire for what the relaxed loads saw: only on request (the operands are fetched
-              // from L2 with cp.async.cg after the flag load returned), and
-              // always across GPUs
-              if (DIST || g.strict) __threadfence_system();
+              // acquire for what the relaxed loads saw: only on request (g.strict).  The operands are
+              // fetched from L2 with cp.async.cg after the flag load returned, and L2 is the point of
+              // coherence for this GPU's memory whether the producer is an SM or a peer over NVLink
+              // (DESIGN.md 4.2); a system-scope fence here cost ~20 % of the k loop.
+              if (g.strict) { if (DIST) __threadfence_system(); else __threadfence(); }
               s_task = eP | (eQ << 4) | (yr ? 256 : 0);
               break;
             }
@@ -755,6 +814,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             }
             __nanosleep(20);
           }
+          BA_PROF_ADD(kProfLast);
         }
         __syncthreads();
         const int st = s_task;
@@ -790,7 +850,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         if (ca < eA) ca = eA;
       }
       if (!gemv_done) {
-        wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
+        wait_flag<DIST>(g, &yflag[k], epoch, s_t0, kProfYflag);
         __syncthreads();
         if (tid < NB) {
           yk[tid] = __ldcg(g.rhs + k * NB + tid);
@@ -803,24 +863,27 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           bacc += s;
         }
       }
-      if (cl) {
-        contrib_add(clast);
-        ++cnext;
-      }
       __syncthreads();
     }
-    if (DIST && has_panel) {
-      // peers the k loop was too short for (tasks of the first `world` columns): two round trips in
-      // flight at a time, added in rank order
-      for (; cnext < g.world; cnext += 2) {
-        Frag c0, c1;
-        contrib_load(cnext, c0);
-        if (cnext + 1 < g.world) contrib_load(cnext + 1, c1);
-        contrib_add(c0);
-        if (cnext + 1 < g.world) contrib_add(c1);
-      }
-    }
     BA_TRACE(t, 3);   // k loop done
+    double* const Ws = buf + 3 * kTileDoubles;   // chain: D_j's partial diagonal tile, [col*LDT + row]
+    double vpart = 0.0;
+    if (chain && j > 0) {
+      // D_j was grabbed right before this task and has less to do: its partial tile is (all but
+      // always) there by now.  It is staged into the one operand buffer the panel phase leaves
+      // alone and added to W after the fold, so the L2 latency hides behind the panel phase.
+      wait_flag<DIST>(g, &g.flags[(size_t)T * T + j], epoch, s_t0, kProfDiagFlag);
+      __syncthreads();
+      const double* Wp = g.Wpart + (size_t)j * (NB * NB + NB);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int chunk = it * kSolveThreads + tid;
+        const int m = chunk >> 5, r2 = (chunk & 31) * 2;
+        cp_async16(Ws + m * LDT + r2, Wp + (size_t)m * NB + r2);
+      }
+      cp_async_commit();
+      if (tid < NB) vpart = __ldcg(Wp + NB * NB + tid);
+    }
 
     double* const Cs = buf;                       // [m][row] = C[row][m]      (A operand)
     double* const Bs = buf + kTileDoubles;        // [m][c]   = Linv_pj[c][m]  (B operand), filled block by block
@@ -905,7 +968,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
               }
             // only when nothing is ready yet, spin on the next block
             if (e == cb) e = spin_expired(g, pspins, s_t0) ? 8 : -1;   // nothing new: flush the pending publication, fold pending column blocks into W
-            else if (DIST || g.strict) __threadfence_system();          // acquire for the rows the scan found
+            else if (g.strict) { if (DIST) __threadfence_system(); else __threadfence(); }   // acquire for the rows the scan found
             s_task = e;
           }
           e = __shfl_sync(0xffffffffu, e, 0);
@@ -918,6 +981,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         __syncthreads();
         const int ce = s_task;
         if (ce < 0) {   // CTA-uniform
+#ifdef BA_SOLVE_PROF
+          if (tid == 32) atomicAdd(&g_prof[g.rank & 7][kProfPanel], 400ull);   // ~ one idle round (scan + sleep + barriers)
+#endif
           have_snap = false;
           const bool idle = pub_lo < 0 && !(chain && ub < cb);
           if (pub_lo >= 0) {
@@ -1041,6 +1107,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // tile (pi, pj) of L is complete.  The last group was stored directly; warp 1 releases it
       // (warp 0 starts the sweep of a chain task, warp 7 has the most of W left to fold; the
       // fence stalls global traffic only, and the rest of a chain task works out of shared memory).
+      if (chain) cp_async_wait<0>();   // D_j's partial tile (Ws)
       __syncthreads();
       if (wid == 1) {
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
@@ -1059,11 +1126,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
       }
       if (chain && ub < 8) fold(ub, 8);
+      if (chain) {   // (a chain task with a panel has j > 0)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (c <= r) W.t[c][e] += Ws[(8 * c + 2 * t4 + e) * LDT + 8 * r + gq];
+        bacc += vpart;
+      }
       BA_TRACE(t, 6);   // panel part done
     }
     // warp 1: the tile's bulk copies to the peers have landed -> release its 8 column-block flags and
     // the tile flag on every peer (system scope)
     auto peer_tile_flags = [&]() {
+      BA_PROF_T0();
       bulk_store_wait();
       __threadfence_system();
       __syncwarp();
@@ -1073,6 +1149,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           unsigned int* f = lane < 8 ? pf + solve_rowflag_base(T) + 8 * T + ((size_t)pi * T + pj) * 8 + lane : pf + (size_t)pi * T + pj;
           st_relaxed_sys(f, epoch);
         }
+      if (lane == 0) BA_PROF_ADD(kProfPush);
     };
     if (DIST && has_panel && !chain && wid == 1) peer_tile_flags();
 
@@ -1341,7 +1418,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // forward substitution: y_j = Linv (b_j - sum_{k<j} L_jk y_k); the k = j-1 term comes from
       // the panel tile this task produced itself (still in Ls)
       if (j > 0) {
-        wait_flag<DIST>(g, &yflag[j - 1], epoch, s_t0);
+        wait_flag<DIST>(g, &yflag[j - 1], epoch, s_t0, kProfYflag);
         __syncthreads();
         if (tid < NB) yk[tid] = __ldcg(g.rhs + (j - 1) * NB + tid);
         __syncthreads();
@@ -1376,6 +1453,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
     }
     BA_TRACE(t, 5);   // published
+    if (tid == 0) BA_PROF_ADD(chain ? kProfChainTask : kProfTask);
   }
 
   // ==================================== backward substitution ==============================
@@ -1396,9 +1474,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // everything this task reads except the x_i is long finished when it starts: wait for all of
     // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
-    wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0);   // L_kk^{-1}
-    wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0);                        // y_k
-    for (int i = T - 1; i > k; --i) wait_flag<DIST>(g, &g.flags[(size_t)i * T + k], epoch, s_t0);   // tiles (i, k)
+    wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0, kProfBackward);   // L_kk^{-1}
+    wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0, kProfBackward);                        // y_k
+    for (int i = T - 1; i > k; --i) wait_flag<DIST>(g, &g.flags[(size_t)i * T + k], epoch, s_t0, kProfBackward);   // tiles (i, k)
     __syncthreads();
     {
       const double* LT = g.LinvT + (size_t)k * NB * NB;
@@ -1465,6 +1543,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     }
     BA_TRACE(ntasks + bt, 5);
   }
+#ifdef BA_SOLVE_PROF
+  if (tid == 0) atomicAdd(&g_prof[g.rank & 7][kProfKernel], global_ns() - s_t0);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1477,7 +1558,7 @@ std::vector<int> dist_task_list(int T, int world, int rank, int band) {
   std::vector<double> load(world, 0.0);
   std::vector<int> owner(T, 0);
   auto cost = [](int i, int j) { return (i == j) ? 2.0 * (j > 0 ? j - 1 : 0) + 8.0 : (double)j + 2.0; };
-  for (int j = 0; j < T; ++j) load[0] += cost(j, j);
+  for (int j = 0; j < T; ++j) load[0] += cost(j, j) + (j > 2 ? 0.6 * (j - 2) : 0.0);   // chain + diagonal-update tasks
   std::vector<std::pair<double, int>> rows;
   for (int i = 0; i < T; ++i) {
     double rc = 0.0;
@@ -1498,6 +1579,7 @@ std::vector<int> dist_task_list(int T, int world, int rank, int band) {
   std::vector<int> mine;
   if (rank == 0) mine.push_back(0);   // C_0
   for (int jc = 0; jc + 1 < T; ++jc) {
+    if (rank == 0) mine.push_back(kDiagTask | (jc + 1));          // D_{jc+1}
     if (rank == 0) mine.push_back(((jc + 1) << 16) | (jc + 1));   // C_{jc+1}
     for (int i = jc + 2; i < T; ++i) {
       const int o = (i - jc <= band) ? 0 : owner[i];
@@ -1509,7 +1591,7 @@ std::vector<int> dist_task_list(int T, int world, int rank, int band) {
 
 bool dist_solve_selected(const Context& c) {
   return c.comm_world > 1 && c.comm_buf && c.dist_off != 0 && c.sys_state == kSysLocal && c.dist_min_tiles > 0 &&
-         c.ld / NB >= c.dist_min_tiles && c.ld / NB < 65536;
+         c.ld / NB >= c.dist_min_tiles && c.ld / NB < 16384;
 }
 
 static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st) {
@@ -1541,6 +1623,7 @@ static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st
   g.rhs = g.A + (size_t)ld * ld;
   g.x = c.dC;
   g.LinvT = base + dl.LinvT;
+  g.Wpart = base + dl.wpart;
   g.flags = reinterpret_cast<unsigned int*>(base + dl.flags);
   g.tickets = c.solve_tickets;
   g.status = &c.scalars->status;
@@ -1548,7 +1631,7 @@ static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st
   g.epoch = ++c.dist_epoch;   // collective: every rank calls the distributed solve the same number of times
   g.abort = reinterpret_cast<unsigned int*>(base + dl.abort);
   g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
-  g.strict = 1;
+  g.strict = c.strict_flags;
   g.world = c.comm_world; g.rank = c.comm_rank;
   g.tasks = c.dist_tasks; g.ntasks = c.dist_ntasks;
   for (int p = 0; p < kMaxPeers; ++p) g.base[p] = p < c.comm_world ? c.comm_peer[p] + c.dist_off : nullptr;
@@ -1583,6 +1666,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   g.rhs = c.Adense + (size_t)ld * ld;
   g.x = c.dC;
   g.LinvT = c.LinvT;
+  g.Wpart = c.Wpart;
   g.flags = c.solve_flags;
   g.tickets = c.solve_tickets;
   g.status = &c.scalars->status;
@@ -1595,7 +1679,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
 #ifdef BA_SOLVE_TRACE
   g.trace = c.solve_trace;
 #endif
-  const int ntasks = 1 + T * (T - 1) / 2;
+  const int ntasks = 1 + (T - 1) * (T + 2) / 2;
   int grid = ntasks < c.num_sms ? ntasks : c.num_sms;   // 1 CTA / SM (128 KB smem): all co-resident
   if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
   chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);

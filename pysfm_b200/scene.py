@@ -427,6 +427,12 @@ class DeviceProblem(object):
         self.dist_solve = bool(self.lib.ba_dist_solve_active(self.h))
         return True
 
+    def disconnect_peers(self):
+        """First half of the collective tear-down: unmap the peers' buffers (the caller then
+        synchronises the ranks before any of them destroys its handle)."""
+        if self.peer_comm and getattr(self, "h", None) is not None and self.h.value:
+            self._chk(self.lib.ba_comm_disconnect(self.h), "ba_comm_disconnect")
+
     def disable_peer_comm(self):
         """Back to the caller-owned (torch) system buffer and host-side collectives."""
         if getattr(self, "_torch_sys", None) is not None:

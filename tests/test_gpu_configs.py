@@ -177,7 +177,7 @@ def test_nonfinite_cost_is_reported(cuda_device):
     from pysfm_b200.bundle_adjuster import BundleAdjuster
     from pysfm_b200 import synthetic
     b = synthetic.make_scene(6, 50, 4, seed=33)
-    b.reconstruction[7, 1] = np.nan
+    b._obs_arrays[2][9, 0] = np.nan          # one measurement is NaN
     ba = BundleAdjuster(b, device=cuda_device, verbose=False)
     ba._push(b)
     ba._problem.cost()

@@ -98,9 +98,9 @@ def test_sharded_update_staged_api_and_trajectory(world, collective, tmp_path, c
     assert float(got["cost0_again"]) == float(got["cost0"])
     # staged path against the oracle's stages
     blocks = ba_oracle.prepare(P)
-    assert relerr(got["HCCs"], blocks["HCCs"]) < 1e-9
     assert relerr(got["bPs"], blocks["bPs"]) < 1e-9
     ba_oracle.apply_damping(blocks, 2.0)
+    assert relerr(got["HCCs"], blocks["HCCs"]) < 1e-9     # (saved after apply_damping)
     S, rhs, Vinv = ba_oracle.schur(P, blocks)
     assert relerr(got["S"], S) < 1e-9
     assert relerr(got["rhs"], rhs) < 1e-9

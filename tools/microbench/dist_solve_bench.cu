@@ -5,7 +5,8 @@
 // protocol -- task ownership, contribution sums, tile / Linv / y pushes, flags, start barrier,
 // redundant backward substitution -- without a multi-GPU box; the real NVLink path is covered by
 // tests/test_multi_gpu.py.
-//     dist_solve_bench [n_opt_cam] [virtual ranks] [reps] [band]
+//     dist_solve_bench [n_opt_cam] [virtual ranks] [reps] [band] [strict]
+#define BA_SOLVE_PROF 1
 #include "../../pysfm_b200/csrc/ba_solve.cu"
 
 #include <cmath>
@@ -16,9 +17,10 @@
 
 int main(int argc, char** argv) {
   const int nc = argc > 1 ? atoi(argv[1]) : 199;
-  const int world = argc > 2 ? atoi(argv[2]) : 2;
+  const int world = argc > 2 ? (atoi(argv[2]) < 2 ? 2 : atoi(argv[2])) : 2;
   const int reps = argc > 3 ? atoi(argv[3]) : 5;
   const int band = argc > 4 ? atoi(argv[4]) : 2;
+  const int strict = argc > 5 ? atoi(argv[5]) : 0;
   const int n = 6 * nc, ld = (n + 63) / 64 * 64, T = ld / 64;
   const size_t nblk = (size_t)nc * (nc + 1) / 2, sys_len = nblk * 36 + n;
   std::vector<double> G((size_t)n * 64), A((size_t)n * n), b(n), packed(sys_len);
@@ -59,6 +61,7 @@ int main(int argc, char** argv) {
     c.solve_grid_cap = sms / world;
     c.comm_world = world; c.comm_rank = r; c.dist_off = comm_len; c.dist_min_tiles = 1; c.dist_band = band;
     c.spin_timeout_ms = 4000.0;
+    c.strict_flags = strict;
     CK(cudaMalloc(&c.comm_buf, (comm_len + dl.total) * 8));
     CK(cudaMemset(c.comm_buf, 0, (comm_len + dl.total) * 8));
     c.sys = c.comm_buf;
@@ -88,6 +91,18 @@ int main(int argc, char** argv) {
     for (int r = 0; r < world; ++r) { float ms; cudaEventElapsedTime(&ms, e0[r], e1[r]); worst = std::max(worst, ms); }
     best = std::min(best, worst);
   }
+  {
+    unsigned long long prof[8][16];
+    CK(cudaMemcpyFromSymbol(prof, ba::g_prof, sizeof prof));
+    const char* names[] = {"panel tasks", "wait_k", "last step spin", "panel idle", "diag flag", "tile push", "contrib tail", "y flag",
+                           "backward waits", "barrier", "kernel x CTAs", "chain tasks", "diag tasks"};
+    printf("wait profile, ms summed over CTAs and %d launches (per launch per CTA in brackets, us):\n", reps);
+    for (int r = 0; r < world; ++r) {
+      printf("  rank %d:", r);
+      for (int s2 = 0; s2 < 13; ++s2) printf(" %s %.2f (%.1f);", names[s2], prof[r][s2] * 1e-6, prof[r][s2] * 1e-3 / reps / (sms / world));
+      printf("\n");
+    }
+  }
   int fails = 0;
   std::vector<double> x0(ld);
   for (int r = 0; r < world; ++r) {
@@ -103,7 +118,7 @@ int main(int argc, char** argv) {
     bool same = true;
     if (r == 0) x0 = x; else same = memcmp(x0.data(), x.data(), (size_t)n * 8) == 0;
     printf("rank %d/%d: %d of %d tile tasks, residual %.3e (rel %.3e), status %g, bits %s rank 0\n", r, world, ctx[r].dist_ntasks,
-           1 + T * (T - 1) / 2, rmax, rmax / bmax, sc.status, same ? "==" : "!=");
+           1 + (T - 1) * (T + 2) / 2, rmax, rmax / bmax, sc.status, same ? "==" : "!=");
     if (!(rmax / bmax < 1e-9) || sc.status != 0.0 || !same) ++fails;
   }
   printf("nc=%d n=%d T=%d world=%d band=%d grid=%d/rank: distributed solve %.3f ms (best of %d, max over ranks), %.2f GFLOP/s  %s\n", nc, n, T,

@@ -2,6 +2,7 @@
 // SPD system in the packed block layout, runs launch_solve, checks the residual on the host and
 // prints a per-task timeline.   solve_bench [n_opt_cam] [reps]
 #define BA_SOLVE_TRACE 1
+#define BA_SOLVE_PROF 1
 #include "../../pysfm_b200/csrc/ba_solve.cu"
 
 #include <cstdio>
@@ -40,10 +41,11 @@ int main(int argc, char** argv) {
   ba::Context c;
   c.n_opt_cam = nc; c.n_sys = n; c.ld = ld; c.sys_len = sys_len;
   int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0); c.num_sms = sms;
-  const int ntasks = 1 + T * (T - 1) / 2;
+  const int ntasks = 1 + (T - 1) * (T + 2) / 2;
   CK(cudaMalloc(&c.sys, sys_len * 8)); CK(cudaMemcpy(c.sys, packed.data(), sys_len * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c.Adense, ((size_t)ld * ld + ld) * 8));
   CK(cudaMalloc(&c.LinvT, (size_t)T * 4096 * 8)); CK(cudaMemset(c.LinvT, 0, (size_t)T * 4096 * 8));
+  CK(cudaMalloc(&c.Wpart, (size_t)T * (4096 + 64) * 8));
   CK(cudaMalloc(&c.solve_flags, ba::solve_flag_count(T) * 4)); CK(cudaMemset(c.solve_flags, 0, ba::solve_flag_count(T) * 4));
   CK(cudaMalloc(&c.solve_tickets, 8));
   CK(cudaMalloc(&c.solve_abort, 8)); CK(cudaMemset(c.solve_abort, 0, 8));
@@ -75,6 +77,15 @@ int main(int argc, char** argv) {
   ba::Scalars sc; CK(cudaMemcpy(&sc, c.scalars, sizeof sc, cudaMemcpyDeviceToHost));
   printf("nc=%d n=%d T=%d tasks=%d: solve %.3f ms (best of %d; mean %.3f), residual %.3e (rel %.3e), status %g, %.2f GFLOP/s\n", nc, n, T,
          ntasks, best, reps, mean, rmax, rmax / bmax, sc.status, (double)n * n * n / 3 / (best * 1e-3) / 1e9);
+  {
+    unsigned long long prof[8][16];
+    CK(cudaMemcpyFromSymbol(prof, ba::g_prof, sizeof prof));
+    const char* names[] = {"panel tasks", "wait_k", "last step spin", "panel idle", "diag flag", "tile push", "contrib tail", "y flag",
+                           "backward waits", "barrier", "kernel x CTAs", "chain tasks", "diag tasks"};
+    printf("wait profile (us per launch per CTA):");
+    for (int s2 = 0; s2 < 13; ++s2) printf(" %s %.1f;", names[s2], prof[0][s2] * 1e-3 / reps / sms);
+    printf("\n");
+  }
   // timeline of the last run
   std::vector<unsigned long long> tr((size_t)(ntasks + T) * 8);
   CK(cudaMemcpy(tr.data(), c.solve_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
