@@ -72,7 +72,8 @@ enum {
                                       reduced system has at least this many 64-wide tile rows
                                       (default 32, i.e. >= 2048 camera parameters; 0 = never) */
   BA_OPT_DIST_BAND = 3,            /* distributed solve: tiles with i - j <= band stay on rank 0 */
-  BA_OPT_SOLVE_GRID_CAP = 4        /* at most this many solver CTAs (0 = one per SM) */
+  BA_OPT_SOLVE_GRID_CAP = 4,       /* at most this many solver CTAs (0 = one per SM) */
+  BA_OPT_SOLVER_PROFILE = 5        /* 1: the solver accumulates its wait-time profile (ba_solver_profile) */
 };
 
 enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */
@@ -243,6 +244,15 @@ int ba_triangulate(ba_handle h, void* stream);
 int ba_set_solution(ba_handle h, const double* dC_host, void* stream);
 
 int ba_sync(ba_handle h, void* stream);
+
+/* Diagnostics (the reference has none; SURVEY section 5 lists stage timers as the natural
+ * counterpart of its print statements): nanoseconds, summed over the CTAs of all solver launches
+ * since the last reset, in 16 slots: [0] plain panel tasks, [1] waiting for k-loop operands,
+ * [2] last-step polls, [3] idle rounds waiting for rows of the diagonal inverse, [4] waiting for
+ * the diagonal-update task, [5] raising flags on peers, [6] fetching the peers' contributions,
+ * [7] waiting for y_k, [8] backward-substitution waits, [9] start barrier, [10] whole launch,
+ * [11] chain tasks, [12] diagonal-update tasks.  Needs BA_OPT_SOLVER_PROFILE = 1.  Synchronises. */
+int ba_solver_profile(ba_handle h, unsigned long long* out16_host, int reset, void* stream);
 
 /* Number of kernel launches issued through this handle since creation (bench evidence). */
 long long ba_launch_count(ba_handle h);

@@ -18,7 +18,10 @@ BA_ERR_NONFINITE = 6
 BA_ERR_TIMEOUT = 7
 
 (BA_OPT_SPIN_TIMEOUT_MS, BA_OPT_STRICT_FLAGS, BA_OPT_DIST_SOLVE_MIN_TILES, BA_OPT_DIST_BAND,
- BA_OPT_SOLVE_GRID_CAP) = range(5)
+ BA_OPT_SOLVE_GRID_CAP, BA_OPT_SOLVER_PROFILE) = range(6)
+SOLVER_PROFILE_SLOTS = ["panel_tasks", "wait_k_operands", "last_step_polls", "panel_idle_rounds", "wait_diag_task",
+                        "peer_flags", "peer_contributions", "wait_y", "backward_waits", "start_barrier", "launch",
+                        "chain_tasks", "diag_tasks"]
 
 BA_WANT_BLOCKS = 1
 BA_WANT_SCHUR = 2
@@ -70,6 +73,7 @@ SIGNATURES = {
     "ba_triangulate": (ctypes.c_int, [_vp, _vp]),
     "ba_set_solution": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_sync": (ctypes.c_int, [_vp, _vp]),
+    "ba_solver_profile": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "ba_launch_count": (ctypes.c_longlong, [_vp]),
 }
 

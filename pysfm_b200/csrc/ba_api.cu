@@ -135,6 +135,7 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->solve_flags, ba::solve_flag_count((int)T)) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->solve_abort, (size_t)2) == cudaSuccess &&
+            dev_alloc(&c->solve_prof, (size_t)16) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
             dev_alloc(&c->cam_mask, (size_t)c->ld) == cudaSuccess &&
@@ -159,7 +160,7 @@ int ba_destroy(ba_handle h) {
   DeviceGuard guard__(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->dist_tasks};
+                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->solve_prof, h->dist_tasks};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
@@ -324,6 +325,7 @@ int ba_set_option(ba_handle h, int option, double value) {
       h->dist_band = (int)value;
       break;
     case BA_OPT_SOLVE_GRID_CAP: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->solve_grid_cap = (int)value; break;
+    case BA_OPT_SOLVER_PROFILE: h->solve_prof_on = value != 0.0; break;
     default: return BA_ERR_BAD_ARGUMENT;
   }
   return BA_OK;
@@ -539,6 +541,16 @@ int ba_sync(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   BA_ON_DEVICE(h);
   BA_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return BA_OK;
+}
+
+int ba_solver_profile(ba_handle h, unsigned long long* out16, int reset, void* stream) {
+  if (!h || !out16) return BA_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  BA_ON_DEVICE(h);
+  BA_CUDA(h, cudaMemcpyAsync(out16, h->solve_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (reset) BA_CUDA(h, cudaMemsetAsync(h->solve_prof, 0, 16 * sizeof(unsigned long long), st));
+  BA_CUDA(h, cudaStreamSynchronize(st));
   return BA_OK;
 }
 

@@ -142,6 +142,8 @@ struct Context {
   int strict_flags = 0;                     // BA_OPT_STRICT_FLAGS: release/acquire flag publication in the solver
   int solve_grid_cap = 0;                   // BA_OPT_SOLVE_GRID_CAP: at most this many solver CTAs (0 = one per SM)
   unsigned int* solve_abort = nullptr;      // [1] set by a spin-wait that ran past the deadline
+  unsigned long long* solve_prof = nullptr; // [16] wait-time profile of the solver (ba_solver_profile)
+  bool solve_prof_on = false;               // BA_OPT_SOLVER_PROFILE
 
   long long launches = 0;
   std::string last_error;

@@ -238,16 +238,12 @@ __device__ int g_dbg_producer = 36, g_dbg_consumer = 52;
 #define BA_TRACE_SET(rec, slot, v) do { } while (0)
 #endif
 
-// Optional wait-time profile (tools/microbench/*solve_bench.cu define BA_SOLVE_PROF): nanoseconds
-// the polling thread of each wait site spent waiting, summed over the CTAs of a launch.
-#ifdef BA_SOLVE_PROF
-__device__ unsigned long long g_prof[8][16];   // [rank][site]
-#define BA_PROF_T0() const unsigned long long pt0__ = global_ns()
-#define BA_PROF_ADD(site) atomicAdd(&g_prof[g.rank & 7][(site)], global_ns() - pt0__)
-#else
-#define BA_PROF_T0() do { } while (0)
-#define BA_PROF_ADD(site) do { } while (0)
-#endif
+// Wait-time profile (ba_solver_profile, diagnostics): nanoseconds the polling thread of each wait
+// site spent waiting and the time spent inside tasks, summed over the CTAs of the launches since
+// the last reset.  Off (g.prof == nullptr) unless BA_OPT_SOLVER_PROFILE is set: two uniform
+// branches per wait.
+#define BA_PROF_T0() const unsigned long long pt0__ = g.prof ? global_ns() : 0ull
+#define BA_PROF_ADD(site) do { if (g.prof) atomicAdd(&g.prof[(site)], global_ns() - pt0__); } while (0)
 enum { kProfTask = 0, kProfWaitK = 1, kProfLast = 2, kProfPanel = 3, kProfDiagFlag = 4, kProfPush = 5, kProfContrib = 6,
        kProfYflag = 7, kProfBackward = 8, kProfBarrier = 9, kProfKernel = 10, kProfChainTask = 11, kProfDiagTask = 12 };
 
@@ -264,6 +260,7 @@ struct CholArgs {
   int ld, T;
   unsigned int epoch;
   // ---- robustness ----
+  unsigned long long* __restrict__ prof;   // [16] wait-time profile (nullptr = off)
   unsigned int* __restrict__ abort;   // [1] != 0: some spin-wait (here or on a peer) gave up; every wait falls through
   unsigned long long spin_limit_ns;   // budget of the whole launch for waiting
   int strict;                         // release/acquire publication of the column-block flags (PTX-model clean, slower)
@@ -575,34 +572,35 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // on the first steps of the k loop instead hid the latency but kept 32 more registers live
     // across the tile products: spills in the loop every task spends its life in.)
     const size_t tile_off = (size_t)(pj * NB) * ld + (size_t)pi * NB;
-    auto contrib_load = [&](int p, Frag& c) {
-      const double* Ap = g.base[p] + dl.contrib + tile_off;
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
-            c.v[mi][ni][e] = ld_peer_f64(Ap + (size_t)cc * ld + rr);
-          }
-    };
-    auto contrib_add = [&](const Frag& c) {
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += c.v[mi][ni][e];
-    };
     if (DIST && has_panel) {
       BA_PROF_T0();
-      for (int p = 0; p < g.world; p += 2) {
-        Frag c0, c1;
-        contrib_load(p, c0);
-        if (p + 1 < g.world) contrib_load(p + 1, c1);
-        contrib_add(c0);
-        if (p + 1 < g.world) contrib_add(c1);
+      // nothing else is live yet: every peer's share of a quarter of the fragment in flight at once
+      // (4 round trips per task whatever the number of ranks), summed in rank order
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        double c[kMaxPeers][2][2];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p) {
+          if (p < g.world) {
+            const double* Ap = g.base[p] + dl.contrib + tile_off;
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
+                c[p][ni][e] = ld_peer_f64(Ap + (size_t)cc * ld + rr);
+              }
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p) {
+          if (p < g.world) {
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += c[p][ni][e];
+          }
+        }
       }
       if (tid == 0) BA_PROF_ADD(kProfContrib);
     }
@@ -981,9 +979,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         __syncthreads();
         const int ce = s_task;
         if (ce < 0) {   // CTA-uniform
-#ifdef BA_SOLVE_PROF
-          if (tid == 32) atomicAdd(&g_prof[g.rank & 7][kProfPanel], 400ull);   // ~ one idle round (scan + sleep + barriers)
-#endif
+          if (g.prof && tid == 32) atomicAdd(&g.prof[kProfPanel], 400ull);   // ~ one idle round (scan + sleep + barriers)
           have_snap = false;
           const bool idle = pub_lo < 0 && !(chain && ub < cb);
           if (pub_lo >= 0) {
@@ -1112,17 +1108,23 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       if (wid == 1) {
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
-        if (DIST) {
-          // ... and sends the whole tile, still in Ls, to every peer: 64 bulk copies (one column each)
-          // per peer on the TMA path.  A plain panel task waits for them right here and raises the
-          // tile's flags on the peers; in a chain task warp 1 does that when its row block of the
-          // sweep is finished (peer_tile_flags below), so the sweep starts without the link latency.
-          for (int p = 0; p < g.world; ++p)
-            if (p != g.rank) {
-              double* dst = g.base[p] + dl.L + tile_off;
-              bulk_store_column(dst, g.ld, Ls, lane);
-              bulk_store_column(dst, g.ld, Ls, lane + 32);
-            }
+      }
+      if (DIST) {
+        // ... and the whole tile, still in Ls, goes to every peer with plain 16-byte stores: a warp
+        // store is one 512-byte column, 8 columns per warp and peer, fire and forget (~1 us for the
+        // CTA).  448 bulk copies per tile on the TMA path took ~70 us to ISSUE at 8 ranks and sat in
+        // front of every chain task's sweep.  A plain panel task raises the tile's flags on the peers
+        // right away; in a chain task warp 1 does that when its row block of the sweep is finished
+        // (peer_tile_flags below), so the sweep starts without waiting for the links.
+        for (int p = 0; p < g.world; ++p) {
+          if (p == g.rank) continue;
+          double* dst = g.base[p] + dl.L + tile_off;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int m = 8 * wid + q;
+            const double2 v = *reinterpret_cast<const double2*>(Ls + m * LDT + 2 * lane);
+            *reinterpret_cast<double2*>(dst + (size_t)m * ld + 2 * lane) = v;
+          }
         }
       }
       if (chain && ub < 8) fold(ub, 8);
@@ -1136,11 +1138,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       }
       BA_TRACE(t, 6);   // panel part done
     }
-    // warp 1: the tile's bulk copies to the peers have landed -> release its 8 column-block flags and
-    // the tile flag on every peer (system scope)
+    // warp 1, after a barrier behind every warp's stores of the tile to the peers: release its 8
+    // column-block flags and the tile flag on every peer (system scope; the release is cumulative
+    // over the other warps' stores that the barrier ordered before it)
     auto peer_tile_flags = [&]() {
       BA_PROF_T0();
-      bulk_store_wait();
       __threadfence_system();
       __syncwarp();
       for (int p = 0; p < g.world; ++p)
@@ -1151,7 +1153,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         }
       if (lane == 0) BA_PROF_ADD(kProfPush);
     };
-    if (DIST && has_panel && !chain && wid == 1) peer_tile_flags();
+    if (DIST && has_panel && !chain) {
+      __syncthreads();
+      if (wid == 1) peer_tile_flags();
+    }
 
     if (chain) {
       double* const LT = g.LinvT + (size_t)j * NB * NB;
@@ -1543,9 +1548,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     }
     BA_TRACE(ntasks + bt, 5);
   }
-#ifdef BA_SOLVE_PROF
-  if (tid == 0) atomicAdd(&g_prof[g.rank & 7][kProfKernel], global_ns() - s_t0);
-#endif
+  if (g.prof && tid == 0) atomicAdd(&g.prof[kProfKernel], global_ns() - s_t0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1631,6 +1634,7 @@ static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st
   g.epoch = ++c.dist_epoch;   // collective: every rank calls the distributed solve the same number of times
   g.abort = reinterpret_cast<unsigned int*>(base + dl.abort);
   g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
+  g.prof = c.solve_prof_on ? c.solve_prof : nullptr;
   g.strict = c.strict_flags;
   g.world = c.comm_world; g.rank = c.comm_rank;
   g.tasks = c.dist_tasks; g.ntasks = c.dist_ntasks;
@@ -1674,6 +1678,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   g.epoch = ++c.solve_epoch;   // a fresh epoch per call: flags never need clearing
   g.abort = c.solve_abort;
   g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
+  g.prof = c.solve_prof_on ? c.solve_prof : nullptr;
   g.strict = c.strict_flags;
   g.world = 1; g.rank = 0;
 #ifdef BA_SOLVE_TRACE

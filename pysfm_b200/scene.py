@@ -223,7 +223,8 @@ class DeviceProblem(object):
         for env, opt in (("PYSFM_B200_SPIN_TIMEOUT_MS", _lib.BA_OPT_SPIN_TIMEOUT_MS),
                          ("PYSFM_B200_STRICT_FLAGS", _lib.BA_OPT_STRICT_FLAGS),
                          ("PYSFM_B200_DIST_SOLVE_MIN_TILES", _lib.BA_OPT_DIST_SOLVE_MIN_TILES),
-                         ("PYSFM_B200_DIST_BAND", _lib.BA_OPT_DIST_BAND)):
+                         ("PYSFM_B200_DIST_BAND", _lib.BA_OPT_DIST_BAND),
+                         ("PYSFM_B200_SOLVER_PROFILE", _lib.BA_OPT_SOLVER_PROFILE)):
             if os.environ.get(env):
                 self.set_option(opt, float(os.environ[env]))
 
@@ -480,6 +481,14 @@ class DeviceProblem(object):
         self._chk(self.lib.ba_get_system(self.h, host.ctypes.data_as(ctypes.c_void_p), self.sys_len, self._stream()),
                   "ba_get_system")
         return unpack_system(host[:self.sys_len], self.scene.n_opt_cam)
+
+    def solver_profile(self, reset=True):
+        """{slot: milliseconds summed over the solver's CTAs} since the last reset (diagnostics;
+        needs set_option(BA_OPT_SOLVER_PROFILE, 1))."""
+        out = (ctypes.c_ulonglong * 16)()
+        self._chk(self.lib.ba_solver_profile(self.h, ctypes.cast(out, ctypes.c_void_p), int(bool(reset)), self._stream()),
+                  "ba_solver_profile")
+        return dict((name, out[i] * 1e-6) for i, name in enumerate(_lib.SOLVER_PROFILE_SLOTS))
 
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))

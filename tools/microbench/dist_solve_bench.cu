@@ -6,7 +6,6 @@
 // redundant backward substitution -- without a multi-GPU box; the real NVLink path is covered by
 // tests/test_multi_gpu.py.
 //     dist_solve_bench [n_opt_cam] [virtual ranks] [reps] [band] [strict]
-#define BA_SOLVE_PROF 1
 #include "../../pysfm_b200/csrc/ba_solve.cu"
 
 #include <cmath>
@@ -72,6 +71,8 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&c.dC, ld * 8));
     CK(cudaMalloc(&c.cam_mask, ld));
     CK(cudaMalloc(&c.scalars, sizeof(ba::Scalars))); CK(cudaMemset(c.scalars, 0, sizeof(ba::Scalars)));
+    CK(cudaMalloc(&c.solve_prof, 16 * 8)); CK(cudaMemset(c.solve_prof, 0, 16 * 8));
+    c.solve_prof_on = true;
     CK(cudaStreamCreate(&streams[r]));
   }
   for (int r = 0; r < world; ++r)
@@ -93,7 +94,7 @@ int main(int argc, char** argv) {
   }
   {
     unsigned long long prof[8][16];
-    CK(cudaMemcpyFromSymbol(prof, ba::g_prof, sizeof prof));
+    for (int r = 0; r < world; ++r) CK(cudaMemcpy(prof[r], ctx[r].solve_prof, 16 * 8, cudaMemcpyDeviceToHost));
     const char* names[] = {"panel tasks", "wait_k", "last step spin", "panel idle", "diag flag", "tile push", "contrib tail", "y flag",
                            "backward waits", "barrier", "kernel x CTAs", "chain tasks", "diag tasks"};
     printf("wait profile, ms summed over CTAs and %d launches (per launch per CTA in brackets, us):\n", reps);

@@ -2,7 +2,6 @@
 // SPD system in the packed block layout, runs launch_solve, checks the residual on the host and
 // prints a per-task timeline.   solve_bench [n_opt_cam] [reps]
 #define BA_SOLVE_TRACE 1
-#define BA_SOLVE_PROF 1
 #include "../../pysfm_b200/csrc/ba_solve.cu"
 
 #include <cstdio>
@@ -49,6 +48,8 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&c.solve_flags, ba::solve_flag_count(T) * 4)); CK(cudaMemset(c.solve_flags, 0, ba::solve_flag_count(T) * 4));
   CK(cudaMalloc(&c.solve_tickets, 8));
   CK(cudaMalloc(&c.solve_abort, 8)); CK(cudaMemset(c.solve_abort, 0, 8));
+  CK(cudaMalloc(&c.solve_prof, 16 * 8)); CK(cudaMemset(c.solve_prof, 0, 16 * 8));
+  c.solve_prof_on = true;
   CK(cudaMalloc(&c.dC, ld * 8));
   CK(cudaMalloc(&c.cam_mask, ld));
   CK(cudaMalloc(&c.scalars, sizeof(ba::Scalars))); CK(cudaMemset(c.scalars, 0, sizeof(ba::Scalars)));
@@ -79,7 +80,7 @@ int main(int argc, char** argv) {
          ntasks, best, reps, mean, rmax, rmax / bmax, sc.status, (double)n * n * n / 3 / (best * 1e-3) / 1e9);
   {
     unsigned long long prof[8][16];
-    CK(cudaMemcpyFromSymbol(prof, ba::g_prof, sizeof prof));
+    CK(cudaMemcpy(prof[0], c.solve_prof, 16 * 8, cudaMemcpyDeviceToHost));
     const char* names[] = {"panel tasks", "wait_k", "last step spin", "panel idle", "diag flag", "tile push", "contrib tail", "y flag",
                            "backward waits", "barrier", "kernel x CTAs", "chain tasks", "diag tasks"};
     printf("wait profile (us per launch per CTA):");
