@@ -239,6 +239,22 @@ int ba_retract(ba_handle h, const double* delta_cam_host, const double* delta_pt
  * Bundle.triangulate_all, bundle.py:313-321); overwrites the bound state points [n_pt][3]. */
 int ba_triangulate(ba_handle h, void* stream);
 
+/* Device-side scene packer (set_bundle's selection, bundle_adjuster.py:54-101, applied to the
+ * measurements bundle_io.load read, bundle_io.py:10-27): turns the RAW observation list of the whole
+ * bundle -- raw_track[o], raw_cam[o] (ids), raw_uv[o][2], resident on the device -- plus two look-up
+ * tables (track id -> position in the selection or -1, camera id -> position or -1) and cam_slot
+ * into the point-major CSR arrays of the layout above: pt_ptr [n_pt + 1], obs_cam / obs_track [n_obs],
+ * obs_uv [n_obs][2] (capacity n_raw each), every track's observations ordered by (cam_slot, camera
+ * position).  scratch = 2 n_pt ints.  All pointers are DEVICE pointers except n_obs_out (host; the
+ * call synchronises the stream to return it).  Stateless: no handle.  A sliding-window driver
+ * (window_slam.py:30-39) calls this once per window with new tables; the observation list is
+ * uploaded once. */
+int ba_pack_observations(int device, int n_raw, const int* raw_track_dev, const int* raw_cam_dev,
+                         const double* raw_uv_dev, int n_pt, const int* track_lut_dev,
+                         const int* cam_lut_dev, const int* cam_slot_dev, int* pt_ptr_dev,
+                         int* obs_cam_dev, double* obs_uv_dev, int* obs_track_dev, int* scratch_dev,
+                         int* n_obs_out, void* stream);
+
 /* Overwrite the reduced solution dC from a HOST array [n_opt_cam][6] -- lets the staged
  * Python API call backsubstitute(dC) with a caller-supplied camera update (:316). */
 int ba_set_solution(ba_handle h, const double* dC_host, void* stream);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ba_get_array": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_size_t, _vp]),
     "ba_retract": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "ba_triangulate": (ctypes.c_int, [_vp, _vp]),
+    "ba_pack_observations": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _c_int_p, _vp]),
     "ba_set_solution": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_sync": (ctypes.c_int, [_vp, _vp]),
     "ba_solver_profile": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libba_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
-SOURCES = ["ba_api.cu", "ba_kernels.cu", "ba_solve.cu", "ba_comm.cu"]
+SOURCES = ["ba_api.cu", "ba_kernels.cu", "ba_solve.cu", "ba_comm.cu", "ba_pack.cu"]
 HEADERS = ["ba_math.cuh", "ba_context.h", os.path.join("..", "..", "include", "ba_b200.h")]
 
 NVCC_FLAGS = [

@@ -388,18 +388,16 @@ class Bundle(object):
                                   [track.measurements[i] for i in ids])
 
     def triangulate_all(self, device=None):
-        """Replace every point by its linear triangulation (bundle.py:313-321).  With `device`
-        (e.g. "cuda:0") all tracks are triangulated by one kernel launch (ba_triangulate);
-        without it the reference's per-track host loop runs (numpy mirror in triangulate.py)."""
-        if device is None:
-            self.reconstruction = np.array([self.triangulate(track) for track in self.tracks])
-            return
+        """Replace every point by its linear triangulation (bundle.py:313-321): all tracks by one
+        kernel launch (ba_triangulate) on `device` (default: the current CUDA device).  There is
+        no host loop on this path; `Bundle.triangulate(track)` remains as the reference's
+        single-track helper."""
         from . import scene as _scene
         cams = list(range(len(self.cameras)))
         trks = list(range(self.num_tracks()))
         if np.shape(self.reconstruction) != (len(trks), 3):
             self.reconstruction = np.zeros((len(trks), 3))
-        packed = _scene.pack_scene(self, cams, trks, range(len(cams)), range(len(trks)))
+        packed = _scene.pack_scene_device(self, cams, trks, range(len(cams)), range(len(trks)), device)
         prob = _scene.DeviceProblem(packed, device)
         try:
             prob.triangulate()

@@ -113,13 +113,21 @@ class BundleAdjuster(object):
         assert len(self.optim_camera_ids) == len(self.optim_camera_indices)
 
         self.close()
-        packed = _scene.pack_scene(bundle, self.camera_ids, self.track_ids,
-                                   self.optim_camera_indices, self.optim_track_indices)
         self._world, self._rank = 1, 0
         if self._shard:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 self._world, self._rank = dist.get_world_size(), dist.get_rank()
+        import torch
+        if self._world == 1 and torch.cuda.is_available():
+            # the measurements stay on the device across set_bundle calls (uploaded once per bundle);
+            # the selection is packed there (ba_pack_observations)
+            packed = _scene.pack_scene_device(bundle, self.camera_ids, self.track_ids,
+                                              self.optim_camera_indices, self.optim_track_indices, self._device)
+        else:
+            # sharded: contiguous point ranges are cut from the host image, each rank uploads its own
+            packed = _scene.pack_scene(bundle, self.camera_ids, self.track_ids,
+                                       self.optim_camera_indices, self.optim_track_indices)
         self._packed_full = packed
         self._packed = packed.shard(self._rank, self._world)
         if self._world > 1:

@@ -135,6 +135,7 @@ int ba_create(int device, int n_cam, int n_pt, int n_obs, int n_opt_cam, int n_o
             dev_alloc(&c->solve_flags, ba::solve_flag_count((int)T)) == cudaSuccess &&
             dev_alloc(&c->solve_tickets, (size_t)2) == cudaSuccess &&
             dev_alloc(&c->solve_abort, (size_t)2) == cudaSuccess &&
+            dev_alloc(&c->diag_rep, (size_t)16 * 36 * (size_t)n_opt_cam) == cudaSuccess &&
             dev_alloc(&c->solve_prof, (size_t)16) == cudaSuccess &&
             dev_alloc(&c->delta_cam, (size_t)n_cam * 6) == cudaSuccess &&
             dev_alloc(&c->delta_pt, (size_t)n_pt * 3) == cudaSuccess &&
@@ -160,7 +161,7 @@ int ba_destroy(ba_handle h) {
   DeviceGuard guard__(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->solve_prof, h->dist_tasks};
+                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->solve_prof, h->dist_tasks, h->diag_rep};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)

@@ -109,6 +109,7 @@ struct Context {
   bool elim_attr_set[8] = {false, false, false, false, false, false, false, false};
   bool elim_group_attr_set[2] = {false, false};
   double* rec_scratch = nullptr;   // [n_obs][56] records of long tracks (elimination kernel, REC_GLOBAL)
+  double* diag_rep = nullptr;      // [16][n_opt_cam][36] spread copies of the diagonal blocks (elimination kernel; zero between launches)
   bool backsub_attr_set[3] = {false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
@@ -135,7 +136,7 @@ struct Context {
   int dist_ntasks = 0;
   unsigned int dist_epoch = 0;
   int dist_min_tiles = 32;                  // BA_OPT_DIST_SOLVE_MIN_TILES: distributed solve when ld/64 >= this (0 = never)
-  int dist_band = 2;                        // BA_OPT_DIST_BAND: tiles with i - j <= band stay on rank 0 with the chain tasks
+  int dist_band = 6;                        // BA_OPT_DIST_BAND: tiles with i - j <= band stay on rank 0 with the chain tasks
   bool dist_attr_set = false;
   // robustness knobs of the spin-waits (solver flags, peer barriers)
   double spin_timeout_ms = 10000.0;         // BA_OPT_SPIN_TIMEOUT_MS

@@ -85,6 +85,7 @@ struct ElimArgs {
   double* __restrict__ bC;     // [n_cam][6]  (blocks)
   double* __restrict__ W;      // [n_obs][18] (blocks)
   double* rec_global;          // [n_obs][56] scratch for the records of long tracks (REC_GLOBAL)
+  double* __restrict__ diag_rep;   // [kDiagReplicas][n_opt_cam][36] spread copies of the diagonal blocks (folded by fold_diag_kernel)
   double* __restrict__ partials;
   unsigned int* __restrict__ ticket;
   double* __restrict__ cost_out;
@@ -95,11 +96,22 @@ struct ElimArgs {
 //   Jc [kcap][12] | Wv [kcap][18] | Yv [kcap][18] | jtr [kcap][6] | sb [kcap] (int2 {slot, row base})
 // Strides are chosen so that the 128-bit accesses of a quarter-warp fall into distinct banks:
 // 18 doubles = 9 x 16 B per W/Y record, 38 doubles = 19 x 16 B per staged block.
+// The diagonal block (a, a) of the packed system takes one update per observation of camera a
+// (2,500 at config 2) while an off-diagonal block takes ~100: the same-address FP64 reductions
+// serialise in L2 and cost 37 % of the kernel's reduction rate (tools/microbench/red_bench.cu,
+// "hot diagonal blocks": 4.2e11 adds/s against 5.7e11 for uniformly spread blocks).  The diagonal
+// pairs therefore reduce into one of kDiagReplicas spread copies, chosen per warp, which
+// fold_diag_kernel adds into the packed diagonal blocks (and clears) right after.
+constexpr int kDiagReplicas = 16;
 constexpr int kStageStride = 38;
 constexpr int kStageDoubles = 32 * kStageStride;
 constexpr int kObsRec = 12 + 18 + 18 + 6 + 1;
 __host__ __device__ __forceinline__ int elim_warp_doubles(int kcap) {
   return (kStageDoubles + kObsRec * kcap + 1) & ~1;
+}
+
+__host__ __device__ __forceinline__ size_t packed_diag_block(int a, int nc) {   // index of block (a, a) in the packed triangle
+  return (size_t)a * nc - (size_t)a * (a - 1) / 2;
 }
 
 // q-th pair (a <= b) of a point with k observations, rows a = 0..k-1 holding b = a..k-1
@@ -143,6 +155,7 @@ linearize_eliminate_kernel(const ElimArgs A) {
   const double damp1 = 1.0 + A.damping;
   double* __restrict__ S = A.sys;
   double* __restrict__ rhs = A.sys + A.rhs_off;
+  const int rep_of_warp = (blockIdx.x * warps_per_cta + wid) % kDiagReplicas;
 
   double cost_acc = 0.0;
   // Two-deep software pipeline over the warp's points: the CSR range of the point after next and
@@ -330,7 +343,9 @@ linearize_eliminate_kernel(const ElimArgs A) {
               *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (A.probe != 1) bulk_add_block(S + (size_t)(sa.y + slot_b) * 36, my_stage);
+          double* dst = (a == b) ? A.diag_rep + ((size_t)rep_of_warp * A.n_opt_cam + sa.x) * 36
+                                 : S + (size_t)(sa.y + slot_b) * 36;
+          if (A.probe != 1) bulk_add_block(dst, my_stage);
         }
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -339,6 +354,22 @@ linearize_eliminate_kernel(const ElimArgs A) {
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
+// S(a, a) += sum over the replicas, replicas cleared for the next iteration.  One CTA per camera.
+__global__ void __launch_bounds__(64) fold_diag_kernel(double* __restrict__ S, double* __restrict__ diag_rep, int n_opt_cam) {
+  const int a = blockIdx.x, e = threadIdx.x;
+  if (e >= 36) return;
+  double v[kDiagReplicas];
+#pragma unroll
+  for (int r = 0; r < kDiagReplicas; ++r) v[r] = __ldcg(diag_rep + ((size_t)r * n_opt_cam + a) * 36 + e);
+  double s = 0.0;
+#pragma unroll
+  for (int r = 0; r < kDiagReplicas; ++r) {
+    s += v[r];
+    diag_rep[((size_t)r * n_opt_cam + a) * 36 + e] = 0.0;
+  }
+  S[packed_diag_block(a, n_opt_cam) * 36 + e] += s;
 }
 
 
@@ -983,6 +1014,7 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
     if ((e = cudaMalloc((void**)&c.rec_scratch, (size_t)(c.n_obs > 0 ? c.n_obs : 1) * 56 * sizeof(double))) != cudaSuccess) return e;
   }
   A.rec_global = c.rec_scratch;
+  A.diag_rep = c.diag_rep;
   const size_t per_warp = (size_t)elim_warp_doubles(rec_global ? 0 : kcap) * sizeof(double);
   int warps = (int)(budget / per_warp);
   if (warps > 8) warps = 8;
@@ -1006,6 +1038,10 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
   }
   kern<<<grid, warps * 32, smem, st>>>(A);
   c.launches += 1;
+  if (schur && c.n_opt_cam > 0) {
+    fold_diag_kernel<<<c.n_opt_cam, 64, 0, st>>>(c.sys, c.diag_rep, c.n_opt_cam);
+    c.launches += 1;
+  }
   return cudaGetLastError();
 }
 

@@ -572,35 +572,46 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // on the first steps of the k loop instead hid the latency but kept 32 more registers live
     // across the tile products: spills in the loop every task spends its life in.)
     const size_t tile_off = (size_t)(pj * NB) * ld + (size_t)pi * NB;
+    auto push_tile_to_peers = [&]() {   // all warps; Ls = buf + 2 tiles holds L_{pi,pj} as [m][row]
+      const double* Lsrc = buf + 2 * kTileDoubles;
+      for (int p = 0; p < g.world; ++p) {
+        if (p == g.rank) continue;
+        double* dst = g.base[p] + dl.L + tile_off;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int m = 8 * wid + q;
+          const double2 v = *reinterpret_cast<const double2*>(Lsrc + m * LDT + 2 * lane);
+          *reinterpret_cast<double2*>(dst + (size_t)m * ld + 2 * lane) = v;
+        }
+      }
+    };
     if (DIST && has_panel) {
       BA_PROF_T0();
-      // nothing else is live yet: every peer's share of a quarter of the fragment in flight at once
-      // (4 round trips per task whatever the number of ranks), summed in rank order
+      // The four operand buffers are still free: four peers' tiles are staged into them at once with
+      // cp.async (one loaded NVLink round trip, ~9 us, per FOUR peers; register loads managed one
+      // round trip per quarter of the fragment) and summed in rank order.  (.cg: peer memory is
+      // never held in this GPU's L2, and L1 is bypassed, so every solve sees the fresh contribution.)
+      for (int p0 = 0; p0 < g.world; p0 += 4) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        double c[kMaxPeers][2][2];
+        for (int q = 0; q < 4; ++q)
+          if (p0 + q < g.world) stage_tile(buf + (size_t)q * kTileDoubles, g.base[p0 + q] + dl.contrib + tile_off, ld);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
 #pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p) {
-          if (p < g.world) {
-            const double* Ap = g.base[p] + dl.contrib + tile_off;
+        for (int q = 0; q < 4; ++q) {
+          if (p0 + q < g.world) {
+            const double* Cq = buf + (size_t)q * kTileDoubles;
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
+            for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int rr = R0 + 8 * mi + gq, cc = C0 + 8 * ni + 2 * t4 + e;
-                c[p][ni][e] = ld_peer_f64(Ap + (size_t)cc * ld + rr);
-              }
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                  acc.v[mi][ni][e] += Cq[(C0 + 8 * ni + 2 * t4 + e) * LDT + R0 + 8 * mi + gq];
           }
         }
-#pragma unroll
-        for (int p = 0; p < kMaxPeers; ++p) {
-          if (p < g.world) {
-#pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) acc.v[mi][ni][e] += c[p][ni][e];
-          }
-        }
+        __syncthreads();   // the buffers are free again (next round / the k loop)
       }
       if (tid == 0) BA_PROF_ADD(kProfContrib);
     }
@@ -1109,24 +1120,15 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
         if (lane == 0) st_release(&g.flags[(size_t)pi * T + pj], epoch);
       }
-      if (DIST) {
-        // ... and the whole tile, still in Ls, goes to every peer with plain 16-byte stores: a warp
-        // store is one 512-byte column, 8 columns per warp and peer, fire and forget (~1 us for the
-        // CTA).  448 bulk copies per tile on the TMA path took ~70 us to ISSUE at 8 ranks and sat in
-        // front of every chain task's sweep.  A plain panel task raises the tile's flags on the peers
-        // right away; in a chain task warp 1 does that when its row block of the sweep is finished
-        // (peer_tile_flags below), so the sweep starts without waiting for the links.
-        for (int p = 0; p < g.world; ++p) {
-          if (p == g.rank) continue;
-          double* dst = g.base[p] + dl.L + tile_off;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int m = 8 * wid + q;
-            const double2 v = *reinterpret_cast<const double2*>(Ls + m * LDT + 2 * lane);
-            *reinterpret_cast<double2*>(dst + (size_t)m * ld + 2 * lane) = v;
-          }
-        }
-      }
+      // DIST: the whole tile, still in Ls, goes to every peer with plain 16-byte stores: a warp store
+      // is one 512-byte column, 8 columns per warp and peer, fire and forget.  (448 bulk copies per
+      // tile on the TMA path took ~70 us to ISSUE at 8 ranks.)  A plain panel task does it right here
+      // and raises the tile's flags on the peers; a CHAIN task keeps every remote store for its very
+      // end (push_tile_to_peers after the sweep): a release at gpu scope -- the local row-block flags
+      // of the sweep -- waits for the acknowledgement of every store the warp has in flight, and
+      // with stores on the links that is a loaded NVLink round trip (~9 us) per release on the
+      // critical path of the factorisation.
+      if (DIST && !chain) push_tile_to_peers();
       if (chain && ub < 8) fold(ub, 8);
       if (chain) {   // (a chain task with a panel has j > 0)
 #pragma unroll
@@ -1316,20 +1318,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             LT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = mc0[c];
             LT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = mc1[c];
           }
-          if (DIST) {   // the same rows straight into every peer's copy (fire and forget; flagged below)
-            for (int p = 0; p < g.world; ++p) {
-              if (p == g.rank) continue;
-              double* PT = g.base[p] + dl.LinvT + (size_t)j * NB * NB;
-              PT[(8 * pb + t4) * NB + 8 * pb + gq] = l0;
-              PT[(8 * pb + 4 + t4) * NB + 8 * pb + gq] = l1;
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                if (c >= pb) break;
-                PT[(8 * c + 2 * t4) * NB + 8 * pb + gq] = mc0[c];
-                PT[(8 * c + 2 * t4 + 1) * NB + 8 * pb + gq] = mc1[c];
-              }
-            }
-          }
         }
         if (r == pb && pb > 0) {
           // rows 8 pb .. 8 pb + 7 of L_jj^{-1} are final and this warp has nothing left to do in
@@ -1341,16 +1329,6 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           if (pb == 1 && lane == 1) st_release(&rowflag[(size_t)j * 8 + 0], epoch);
           if (lane == 0) st_release(&rowflag[(size_t)j * 8 + pb], epoch);
           BA_GT(pb, t == g_dbg_producer && lane == 0);
-          if (DIST) {
-            // the peers' copies of these rows (and of row block 0, stored by warp 0 two barriers ago)
-            __threadfence_system();
-            if (lane < g.world && lane != g.rank) {
-              unsigned int* prf = reinterpret_cast<unsigned int*>(g.base[lane] + dl.flags) + solve_rowflag_base(T) + (size_t)j * 8;
-              if (pb == 1) st_relaxed_sys(prf + 0, epoch);
-              st_relaxed_sys(prf + pb, epoch);
-            }
-            if (pb == 1 && has_panel) peer_tile_flags();   // row block 1 is warp 1's: its part of the sweep is over
-          }
         }
         if (r > pb) {
           const double a0 = -Lp[r * TD + gq * TS + t4], a1 = -Lp[r * TD + gq * TS + 4 + t4];
@@ -1408,17 +1386,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           LTs[(e >> 6) * LDT + (e & 63)] = v;
           LT[e] = v;
         }
-        if (DIST) {
-          for (int p = 0; p < g.world; ++p) {
-            if (p == g.rank) continue;
-            double* PT = g.base[p] + dl.LinvT + (size_t)j * NB * NB;
-            for (int e = tid; e < NB * NB; e += kSolveThreads) PT[e] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
-            if (tid == 0) *(g.base[p] + dl.status) = 1.0;   // every rank reports the failed pivot
-          }
-          __threadfence_system();
-        } else {
-          __threadfence();
-        }
+        if (DIST && tid == 0)
+          for (int p = 0; p < g.world; ++p)
+            if (p != g.rank) *(g.base[p] + dl.status) = 1.0;   // every rank reports the failed pivot (flagged with the tile below)
+        __threadfence();
       }
       // forward substitution: y_j = Linv (b_j - sum_{k<j} L_jk y_k); the k = j-1 term comes from
       // the panel tile this task produced itself (still in Ls)
@@ -1434,6 +1405,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
           bacc += s;
         }
       }
+      double yval = 0.0;
       if (tid < NB) tvec[tid] = rhs_j - bacc;
       __syncthreads();
       // (the 8x8 tiles of LTs above the block diagonal were never written: stop at the diagonal tile)
@@ -1443,17 +1415,40 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
 #pragma unroll 8
         for (int m = 0; m < mend; ++m) s += LTs[m * LDT + tid] * tvec[m];
         g.rhs[j * NB + tid] = s;
-        if (DIST)
-          for (int p = 0; p < g.world; ++p)
-            if (p != g.rank) (g.base[p] + dl.L + ld * ld)[j * NB + tid] = s;   // every rank substitutes backwards on its own
+        yval = s;
       }
       __syncthreads();
-      if (tid == 0) {
-        st_release(&yflag[j], epoch);
-        if (DIST) {
+      if (tid == 0) st_release(&yflag[j], epoch);
+      if (DIST) {
+        // Everything this chain task produced goes to the peers NOW, behind the local critical path:
+        // its panel tile (Ls), the inverse of the diagonal tile (lower block triangle of LTs; what
+        // lies above was never written here and stays zero over there) and y_j.
+        BA_PROF_T0();
+        if (has_panel) push_tile_to_peers();
+        for (int p = 0; p < g.world; ++p) {
+          if (p == g.rank) continue;
+          double* PT = g.base[p] + dl.LinvT + (size_t)j * NB * NB;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int m = 8 * wid + q;
+            if ((lane >> 2) >= wid)    // columns 2 lane, 2 lane + 1 lie in a block on or below the diagonal block of row m
+              *reinterpret_cast<double2*>(PT + (size_t)m * NB + 2 * lane) = *reinterpret_cast<const double2*>(LTs + m * LDT + 2 * lane);
+          }
+          if (tid < NB) (g.base[p] + dl.L + ld * ld)[j * NB + tid] = yval;   // every rank substitutes backwards on its own
+        }
+        __syncthreads();
+        if (wid == 1) {
           __threadfence_system();
-          for (int p = 0; p < g.world; ++p)
-            if (p != g.rank) st_relaxed_sys(reinterpret_cast<unsigned int*>(g.base[p] + dl.flags) + (size_t)T * T + T + j, epoch);
+          __syncwarp();
+          for (int p = 0; p < g.world; ++p) {
+            if (p == g.rank) continue;
+            unsigned int* pf = reinterpret_cast<unsigned int*>(g.base[p] + dl.flags);
+            if (has_panel && lane < 8) st_relaxed_sys(pf + solve_rowflag_base(T) + 8 * T + ((size_t)pi * T + pj) * 8 + lane, epoch);
+            if (has_panel && lane == 8) st_relaxed_sys(pf + (size_t)pi * T + pj, epoch);
+            if (lane >= 16 && lane < 24) st_relaxed_sys(pf + solve_rowflag_base(T) + (size_t)j * 8 + (lane - 16), epoch);
+            if (lane == 24) st_relaxed_sys(pf + (size_t)T * T + T + j, epoch);
+          }
+          if (lane == 0) BA_PROF_ADD(kProfPush);
         }
       }
     }

@@ -15,11 +15,33 @@ from . import _lib
 
 
 class PackedScene(object):
-    """Host-side SoA image of the selected sub-problem."""
+    """SoA image of the selected sub-problem.  Cameras, points and slots are host arrays (a few KB
+    to a few MB, they change every iteration anyway); the observation arrays -- pt_ptr, obs_cam,
+    obs_uv, obs_track -- are host arrays when the host packer built them (pack_scene) and DEVICE
+    tensors (`dev`) when the device packer did (pack_scene_device); in that case the host views
+    are downloaded on first use (tests, the dense-HCPs property), never on the product path."""
     __slots__ = ("camera_ids", "track_ids", "optim_camera_indices", "optim_track_indices",
                  "K", "model_kind", "model_params", "cam_R", "cam_t", "pts",
-                 "pt_ptr", "obs_cam", "obs_uv", "obs_track", "cam_slot", "pt_slot",
+                 "_pt_ptr", "_obs_cam", "_obs_uv", "_obs_track", "cam_slot", "pt_slot",
+                 "dev", "_n_obs",
                  "shard_lo", "shard_obs_lo", "shard_opt_lo")   # position of a shard inside the whole selection
+
+    def __init__(self):
+        self.dev = None
+        self._pt_ptr = self._obs_cam = self._obs_uv = self._obs_track = None
+        self._n_obs = None
+
+    def _host(self, name):
+        v = getattr(self, "_" + name)
+        if v is None and self.dev is not None:
+            v = self.dev[name].cpu().numpy()
+            setattr(self, "_" + name, v)
+        return v
+
+    pt_ptr = property(lambda self: self._host("pt_ptr"), lambda self, v: setattr(self, "_pt_ptr", v))
+    obs_cam = property(lambda self: self._host("obs_cam"), lambda self, v: setattr(self, "_obs_cam", v))
+    obs_uv = property(lambda self: self._host("obs_uv"), lambda self, v: setattr(self, "_obs_uv", v))
+    obs_track = property(lambda self: self._host("obs_track"), lambda self, v: setattr(self, "_obs_track", v))
 
     @property
     def n_cam(self):
@@ -31,7 +53,7 @@ class PackedScene(object):
 
     @property
     def n_obs(self):
-        return int(self.obs_cam.shape[0])
+        return int(self._n_obs) if self._n_obs is not None else int(self.obs_cam.shape[0])
 
     @property
     def n_opt_cam(self):
@@ -131,6 +153,99 @@ def pack_scene(bundle, camera_ids, track_ids, optim_camera_indices, optim_track_
     return s
 
 
+_RAW_CACHE = {}
+
+
+def _raw_observations_on_device(bundle, device):
+    """(raw_track, raw_cam, raw_uv) of the WHOLE bundle as device tensors, uploaded once per bundle
+    and device and shared by every bundle that shares the measurements (clone_params copies the
+    parameters, not the tracks: bundle.py:301-310)."""
+    import torch
+    fast = getattr(bundle, "_obs_arrays", None)
+    if fast is not None:
+        holder, key_obj = fast, fast
+    else:
+        holder, key_obj = None, bundle.tracks
+    key = (id(key_obj), str(device))
+    hit = _RAW_CACHE.get(key)
+    if hit is not None and hit[0] is key_obj:
+        return hit[1]
+    if holder is not None:
+        o_cam, o_trk, o_uv = holder
+    else:
+        t_list, c_list, uv_list = [], [], []
+        for j, track in enumerate(bundle.tracks):
+            for cid, z in track.measurements.items():
+                t_list.append(j)
+                c_list.append(cid)
+                uv_list.append(z)
+        o_trk = np.asarray(t_list, dtype=np.int64)
+        o_cam = np.asarray(c_list, dtype=np.int64)
+        o_uv = np.asarray(uv_list, dtype=np.float64).reshape(-1, 2)
+    n = len(o_cam)
+    raw = (torch.as_tensor(np.ascontiguousarray(o_trk, dtype=np.int32)).to(device),
+           torch.as_tensor(np.ascontiguousarray(o_cam, dtype=np.int32)).to(device),
+           torch.as_tensor(np.ascontiguousarray(o_uv, dtype=np.float64).reshape(-1)).to(device) if n
+           else torch.zeros(2, dtype=torch.float64, device=device))
+    while len(_RAW_CACHE) >= 4:         # a handful of resident measurement lists at most
+        _RAW_CACHE.pop(next(iter(_RAW_CACHE)))
+    _RAW_CACHE[key] = (key_obj, raw)    # (holding key_obj keeps its id from being reused)
+    return raw
+
+
+def pack_scene_device(bundle, camera_ids, track_ids, optim_camera_indices, optim_track_indices, device):
+    """pack_scene with the observation arrays built ON THE DEVICE (ba_pack_observations): the raw
+    measurement list of the bundle is uploaded once (and cached on the bundle), a selection costs
+    two look-up tables and four small kernels.  Same layout, same order as pack_scene."""
+    import torch
+    lib = _lib.load()
+    device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    s = PackedScene()
+    s.camera_ids = list(camera_ids)
+    s.track_ids = list(track_ids)
+    s.optim_camera_indices = [int(i) for i in optim_camera_indices]
+    s.optim_track_indices = [int(i) for i in optim_track_indices]
+    nc, nt = len(s.camera_ids), len(s.track_ids)
+    s.K = np.ascontiguousarray(np.asarray(bundle.K, dtype=np.float64).reshape(9))
+    s.model_kind, s.model_params = bundle.sensor_model.device_params()
+    s.model_params = np.ascontiguousarray(s.model_params, dtype=np.float64)
+    s.cam_R, s.cam_t = bundle.camera_arrays(s.camera_ids)
+    s.pts = np.ascontiguousarray(np.asarray(bundle.reconstruction, dtype=np.float64)[s.track_ids])
+    s.cam_slot = np.full(nc, -1, dtype=np.int32)
+    s.cam_slot[s.optim_camera_indices] = np.arange(len(s.optim_camera_indices), dtype=np.int32)
+    s.pt_slot = np.full(nt, -1, dtype=np.int32)
+    s.pt_slot[s.optim_track_indices] = np.arange(len(s.optim_track_indices), dtype=np.int32)
+    s.shard_lo = s.shard_obs_lo = s.shard_opt_lo = 0
+
+    raw_track, raw_cam, raw_uv = _raw_observations_on_device(bundle, device)
+    n_raw = int(raw_cam.shape[0])
+    cam_lut = np.full(max(len(bundle.cameras), 1), -1, dtype=np.int32)
+    cam_lut[np.asarray(s.camera_ids, dtype=np.int64)] = np.arange(nc, dtype=np.int32)
+    trk_lut = np.full(max(bundle.num_tracks(), 1), -1, dtype=np.int32)
+    trk_lut[np.asarray(s.track_ids, dtype=np.int64)] = np.arange(nt, dtype=np.int32)
+    up = lambda a: torch.as_tensor(a).to(device)
+    cam_lut_t, trk_lut_t, cam_slot_t = up(cam_lut), up(trk_lut), up(s.cam_slot)
+    cap = max(n_raw, 1)
+    pt_ptr = torch.empty(nt + 1, dtype=torch.int32, device=device)
+    obs_cam = torch.empty(cap, dtype=torch.int32, device=device)
+    obs_track = torch.empty(cap, dtype=torch.int32, device=device)
+    obs_uv = torch.empty(2 * cap, dtype=torch.float64, device=device)
+    scratch = torch.empty(2 * nt, dtype=torch.int32, device=device)
+    n_obs = ctypes.c_int(0)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    rc = lib.ba_pack_observations(dev_index, n_raw, vp(raw_track), vp(raw_cam), vp(raw_uv), nt, vp(trk_lut_t), vp(cam_lut_t),
+                                  vp(cam_slot_t), vp(pt_ptr), vp(obs_cam), vp(obs_uv), vp(obs_track), vp(scratch),
+                                  ctypes.byref(n_obs), stream)
+    _lib.check(None, rc, "ba_pack_observations")
+    n = int(n_obs.value)
+    s._n_obs = n
+    s.dev = dict(pt_ptr=pt_ptr, obs_cam=obs_cam[:n], obs_track=obs_track[:n], obs_uv=obs_uv[:2 * n].view(-1, 2),
+                 cam_slot=cam_slot_t, _keep=(raw_track, raw_cam, raw_uv))
+    return s
+
+
 def packed_system_index(n_opt_cam):
     """(rows, cols) of the dense reduced-system entry stored at every slot of the packed block
     triangle (include/ba_b200.h): 6x6 blocks (a, b), a <= b, block rows back to back, 36
@@ -180,9 +295,15 @@ class DeviceProblem(object):
         self.n_sys = 6 * scene.n_opt_cam
         self.ld = int(self.lib.ba_system_ld(self.n_sys))
         tt = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
-        self.pt_ptr = tt(scene.pt_ptr, torch.int32)
-        self.obs_cam = tt(scene.obs_cam, torch.int32) if scene.n_obs else torch.zeros(1, dtype=torch.int32, device=dev)
-        self.obs_uv = tt(scene.obs_uv, torch.float64) if scene.n_obs else torch.zeros(2, dtype=torch.float64, device=dev)
+        if scene.dev is not None and scene.dev["pt_ptr"].device == dev:
+            # built on this device by pack_scene_device: nothing to upload
+            self.pt_ptr = scene.dev["pt_ptr"]
+            self.obs_cam = scene.dev["obs_cam"] if scene.n_obs else torch.zeros(1, dtype=torch.int32, device=dev)
+            self.obs_uv = scene.dev["obs_uv"] if scene.n_obs else torch.zeros(2, dtype=torch.float64, device=dev)
+        else:
+            self.pt_ptr = tt(scene.pt_ptr, torch.int32)
+            self.obs_cam = tt(scene.obs_cam, torch.int32) if scene.n_obs else torch.zeros(1, dtype=torch.int32, device=dev)
+            self.obs_uv = tt(scene.obs_uv, torch.float64) if scene.n_obs else torch.zeros(2, dtype=torch.float64, device=dev)
         self.cam_slot = tt(scene.cam_slot, torch.int32)
         self.pt_slot = tt(scene.pt_slot, torch.int32)
         # each parameter set is ONE flat allocation [R | t | x] (views below): a host-driven trial

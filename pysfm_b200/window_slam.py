@@ -29,18 +29,23 @@ def run(complete_bundle, window_size, num_to_freeze=2, pdf_pattern=None, num_tra
     camera_mask = np.arange(window_size) < num_to_freeze   # noqa: F841  (unused in the reference too)
     track_ids = list(range(num_tracks))
     cur_bundle = complete_bundle
+    # ONE adjuster for the whole run.  The measurements of the complete bundle are uploaded by the
+    # first set_bundle and stay on the device (every later bundle shares them: optimize() clones
+    # parameters, not tracks); a window costs two look-up tables, the device packer and the window's
+    # camera / point parameters.  The reference deep-copies the bundle per window only to keep the
+    # pose of the window's first camera (window_slam.py:32,44): that camera is copied instead.
+    ba = BundleAdjuster(device=device, verbose=verbose)
     for i in range(0, len(complete_bundle.cameras) - window_size + 1):
         if verbose:
             print('\n\n==============\nWINDOW: [%d..%d]\n' % (i, i + window_size))
-        prev_bundle = deepcopy(cur_bundle)
+        prev_camera = deepcopy(cur_bundle.cameras[i])
         camera_ids = list(range(i, i + window_size))
-        ba = BundleAdjuster(device=device, verbose=verbose)
         ba.set_bundle(cur_bundle, camera_ids=camera_ids, track_ids=track_ids)
         ba.optimize()
         cur_bundle = ba.bundle
         next_camera_id = i + window_size
         if next_camera_id < len(cur_bundle.cameras):
-            geometry.propagate_pose_update_inplace(prev_bundle.cameras[i], cur_bundle.cameras[i],
+            geometry.propagate_pose_update_inplace(prev_camera, cur_bundle.cameras[i],
                                                    cur_bundle.cameras[i])
         if on_window is not None:
             on_window(i, ba)
@@ -54,7 +59,7 @@ if __name__ == '__main__':
     print('Loading bundle...')
     bundle = bundle_io.load(sys.argv[1], sys.argv[2])
     print('Triangulating initial points...')
-    bundle.triangulate_all()
+    bundle.triangulate_all()          # one kernel launch (ba_triangulate)
     print('Cameras:', len(bundle.cameras))
     print('Tracks:', len(bundle.tracks))
     print('Window Size:', window_size)

@@ -195,3 +195,71 @@ def test_handle_on_another_device_leaves_the_current_device_alone():
     ba = BundleAdjuster(synthetic.make_scene(6, 50, 4, seed=34), device="cuda:1", verbose=False)
     ba.compute_update(1.0)
     assert torch.cuda.current_device() == 0
+
+
+def _assert_same_packing(bundle, camera_ids, track_ids, opt_cam, opt_trk, device):
+    from pysfm_b200 import scene
+    host = scene.pack_scene(bundle, camera_ids, track_ids, opt_cam, opt_trk)
+    dev = scene.pack_scene_device(bundle, camera_ids, track_ids, opt_cam, opt_trk, device)
+    assert dev.n_obs == host.n_obs
+    assert np.array_equal(dev.pt_ptr, host.pt_ptr)
+    assert np.array_equal(dev.obs_cam, host.obs_cam)
+    assert np.array_equal(dev.obs_track, host.obs_track)
+    assert np.array_equal(dev.obs_uv, host.obs_uv)
+    assert np.array_equal(dev.cam_slot, host.cam_slot) and np.array_equal(dev.pt_slot, host.pt_slot)
+
+
+def test_device_packer_matches_host_packer(cuda_device):
+    """ba_pack_observations (count / scan / scatter / per-track sort on the device) against the numpy
+    packer: whole bundles, camera / track subsets in shuffled order, fixed cameras in the middle of
+    the list, object-backed bundles (Track dicts), empty selections of observations."""
+    from pysfm_b200 import synthetic
+    rs = np.random.RandomState(3)
+    b = synthetic.make_scene(40, 3000, 9, seed=51)
+    _assert_same_packing(b, list(range(40)), list(range(3000)), list(range(1, 40)), list(range(3000)), cuda_device)
+    cams = [int(c) for c in rs.permutation(40)[:23]]
+    trks = [int(t) for t in rs.permutation(3000)[:1700]]
+    opt_cam = sorted(int(i) for i in rs.permutation(23)[:15])
+    opt_trk = sorted(int(i) for i in rs.permutation(1700)[:900])
+    _assert_same_packing(b, cams, trks, opt_cam, opt_trk, cuda_device)
+    # the same bundle again: the raw observation list must not be uploaded a second time
+    from pysfm_b200 import scene
+    import torch
+    dev = torch.device(cuda_device)
+    ptrs = [t.data_ptr() for t in scene._raw_observations_on_device(b, dev)]
+    _assert_same_packing(b, cams[:7], trks[:50], [1, 2, 3], list(range(50)), cuda_device)
+    assert [t.data_ptr() for t in scene._raw_observations_on_device(b, dev)] == ptrs
+    c = b.clone_params()            # shares the measurements: shares the device copy
+    assert [t.data_ptr() for t in scene._raw_observations_on_device(c, dev)] == ptrs
+    # object-backed bundle (the reference's fixture: Track objects with measurement dicts)
+    from pysfm_b200.bundle import Bundle
+    ao = synthetic.make_arrays(6, 40, 6, seed=53)
+    table = ao["obs_uv"].reshape(40, 6, 2).transpose(1, 0, 2)          # [camera][track][2]
+    mask = rs.rand(6, 40) < 0.8
+    mask[0] = True
+    bo = Bundle.FromArrays(ao["K"], ao["Rs"], ao["ts"], ao["pts"], table, mask)
+    _assert_same_packing(bo, list(range(6)), list(range(40)), list(range(1, 6)), list(range(40)), cuda_device)
+    _assert_same_packing(bo, [4, 1, 3], list(range(5, 30)), [0, 2], list(range(0, 25, 2)), cuda_device)
+    # a selection whose cameras see nothing of the selected tracks
+    a = synthetic.make_arrays(6, 30, 2, seed=52)
+    from pysfm_b200.bundle import Bundle as B2
+    b2 = B2.FromObservationArrays(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"])
+    seen = set(int(c) for c in a["obs_cam"][a["obs_track"] == 0])
+    unseen = [c for c in range(6) if c not in seen][:2]
+    if len(unseen) == 2:
+        _assert_same_packing(b2, unseen, [0], [1], [0], cuda_device)
+
+
+def test_window_driver_uploads_the_measurements_once(cuda_device):
+    """window_slam.run keeps ONE uploaded observation list for all windows: the device
+    tensors behind every window's packed scene are views of the same allocation."""
+    from pysfm_b200 import window_slam, scene
+    g = load_golden("window_slam")
+    b = golden_bundle(g)
+    ptrs = []
+
+    def hook(i, ba):
+        keep = ba._packed.dev["_keep"]
+        ptrs.append(tuple(t.data_ptr() for t in keep))
+    window_slam.run(b, int(g["win_size"]), device=cuda_device, verbose=False, on_window=hook)
+    assert len(ptrs) >= 2 and len(set(ptrs)) == 1

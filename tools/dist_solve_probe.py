@@ -52,6 +52,13 @@ def main():
     share = torch.as_tensor(packed / world).to(dev)
     ba._push(b)
     times = []
+    clocks = []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        nv = pynvml.nvmlDeviceGetHandleByIndex(local)
+    except Exception:
+        nv = None
     p.solver_profile(reset=True)
     for it in range(args.reps + 1):
         p.linearize_eliminate(10.0, 1e-5, _lib.BA_WANT_SCHUR)    # (marks the system as a fresh local contribution)
@@ -62,6 +69,10 @@ def main():
         e0.record()
         p.solve(None)
         e1.record()
+        if nv is not None:      # SM clock while the solve is running
+            import time
+            time.sleep(0.002)
+            clocks.append(pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM))
         torch.cuda.synchronize(dev)
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -74,7 +85,7 @@ def main():
     prof = p.solver_profile()
     parts = [None] * world
     dist.all_gather_object(parts, dict(rank=rank, status=status, x_hash=float(np.sum(x * np.arange(1, n + 1))), finite=bool(np.all(np.isfinite(x))),
-                                       prof=prof))
+                                       prof=prof, clocks=clocks))
     if rank == 0:
         ok = all(q["status"] == 0 and q["finite"] and q["x_hash"] == parts[0]["x_hash"] for q in parts)
         res = None
@@ -87,7 +98,7 @@ def main():
             ok = ok and res < 1e-9
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         out = {"n": n, "tiles": p.ld // 64, "world": world, "band": args.band, "strict": args.strict, "ms_best": min(times), "ms_all": times,
-               "fp64_tflops": n ** 3 / 3.0 / (min(times) * 1e-3) / 1e12, "ok": ok, "residual_rel": res,
+               "fp64_tflops": n ** 3 / 3.0 / (min(times) * 1e-3) / 1e12, "ok": ok, "residual_rel": res, "sm_mhz_during_solve": [q["clocks"] for q in parts],
                "profile_us_per_launch_per_cta": [dict((k, round(v * 1e3 / args.reps / sms, 1)) for k, v in q["prof"].items()) for q in parts]}
         print(json.dumps(out))
     dist.barrier()
