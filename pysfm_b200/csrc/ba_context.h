@@ -111,6 +111,7 @@ struct Context {
   double* rec_scratch = nullptr;   // [n_obs][56] records of long tracks (elimination kernel, REC_GLOBAL)
   double* diag_rep = nullptr;      // [16][n_opt_cam][36] spread copies of the diagonal blocks (elimination kernel; zero between launches)
   bool backsub_attr_set[3] = {false, false, false};
+  bool backsub_tile_attr_set[3] = {false, false, false};
   double* dP = nullptr;     // [n_pt][3]   point update (rows of non-updated tracks are zero; inside io_out)
   double* obs_r = nullptr;  // [n_obs][2]  lazily allocated (ba_eval_observations)
   double* obs_Jc = nullptr; // [n_obs][12]
@@ -142,6 +143,7 @@ struct Context {
   double spin_timeout_ms = 10000.0;         // BA_OPT_SPIN_TIMEOUT_MS
   int strict_flags = 0;                     // BA_OPT_STRICT_FLAGS: release/acquire flag publication in the solver
   int solve_grid_cap = 0;                   // BA_OPT_SOLVE_GRID_CAP: at most this many solver CTAs (0 = one per SM)
+  int split_min_tiles = 32;                 // diagonal-update tasks take over part of the chain tasks from this many tile rows on
   unsigned int* solve_abort = nullptr;      // [1] set by a spin-wait that ran past the deadline
   unsigned long long* solve_prof = nullptr; // [16] wait-time profile of the solver (ba_solver_profile)
   bool solve_prof_on = false;               // BA_OPT_SOLVER_PROFILE

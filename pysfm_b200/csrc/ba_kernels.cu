@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(192, 2) eliminate_group_kernel(const ElimArgs 
                 *reinterpret_cast<double2*>(my_stage + rr * 6 + cc) = make_double2(v[cc], v[cc + 1]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_add_block(S + (size_t)(rowbase + slot) * 36, my_stage);
+            bulk_add_block(A.diag_rep + ((size_t)((blockIdx.x * warps_per_cta + wid) % kDiagReplicas) * A.n_opt_cam + slot) * 36, my_stage);
           }
         } else {
           int idx = q - n, j = 0;
@@ -814,6 +814,193 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
   grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Back-substitution, TILE-STREAMED (the default whenever the cameras fit in shared memory and no
+// track is longer than 64 views).  backsub_cost_kernel above walks a dependent chain of global
+// loads per point (pt_ptr -> obs_cam -> slot -> obs_uv -> Vinv / bP) and ran at 6.6 % of the HBM
+// peak.  Here a CTA owns CHUNKS of kTilePts consecutive points: the point-major CSR makes every
+// array of a chunk one contiguous range, so the whole chunk -- CSR offsets, points, slots, Vinv,
+// bP and up to kTileObs observation records -- is fetched with independent, coalesced loads into
+// registers while the PREVIOUS chunk is being computed out of shared memory, and parked in shared
+// memory at the top of the next iteration (the bounds of the chunk after next travel one iteration
+// further ahead).  All arithmetic then reads shared memory only; the results (dP, candidate point)
+// are the only global stores.  Cameras, their candidate poses, dC and slots live in shared memory
+// as in the SC variant above.
+constexpr int kTilePts = 32;
+constexpr int kTileObs = 512;
+
+struct TileStage {     // shared-memory image of one chunk
+  int ptr[kTilePts + 1];
+  int slot[kTilePts];
+  double x[3 * kTilePts];
+  double Vi[9 * kTilePts];
+  double bP[3 * kTilePts];
+  int cam[kTileObs];
+  double2 uv[kTileObs];
+};
+
+template <int G>
+__global__ void __launch_bounds__(256, 2) backsub_tile_kernel(const BacksubArgs A, int P) {
+  extern __shared__ __align__(16) double cam_sm[];   // cameras as in backsub_cost_kernel<G, true>, then the stage
+  const ObsArgs& o = A.o;
+  const double* const dC_sm = cam_sm + 24 * o.n_cam;
+  int* const slot_sm = reinterpret_cast<int*>(cam_sm + 30 * o.n_cam);
+  TileStage& S = *reinterpret_cast<TileStage*>(cam_sm + ((31 * o.n_cam + 2) & ~1));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  constexpr int NG = 32 / G;
+  const int sub = lane / G, gl = lane % G;
+  const int n_chunks = (o.n_pt + P - 1) / P;
+
+  // ---- chunk pipeline, part 1: bounds two chunks ahead, data one chunk ahead (registers) ----
+  auto bounds = [&](int c, int& p0, int& np, int& ob0, int& nob) {
+    p0 = c * P;
+    np = 0; ob0 = 0; nob = 0;
+    if (c < n_chunks) {
+      np = (o.n_pt - p0 < P) ? o.n_pt - p0 : P;
+      ob0 = __ldg(o.pt_ptr + p0);
+      nob = __ldg(o.pt_ptr + p0 + np) - ob0;
+    }
+  };
+  int r_ptr = 0, r_slot = -1, r_cam0 = 0, r_cam1 = 0;
+  double r_x = 0.0, r_Vi0 = 0.0, r_Vi1 = 0.0, r_bP = 0.0;
+  double2 r_uv0 = make_double2(0.0, 0.0), r_uv1 = make_double2(0.0, 0.0);
+  auto fetch = [&](int p0, int np, int ob0, int nob) {   // independent loads of one chunk, this thread's share
+    if (np > 0 && tid <= np) r_ptr = __ldcs(o.pt_ptr + p0 + tid);   // (np == 0: past the last chunk, nothing to fetch)
+    if (tid < np) r_slot = __ldcs(o.pt_slot + p0 + tid);
+    if (tid < 3 * np) { r_x = __ldcs(o.pts + 3 * (size_t)p0 + tid); r_bP = __ldcs(A.bP + 3 * (size_t)p0 + tid); }
+    if (tid < 9 * np) r_Vi0 = __ldcs(A.Vinv + 9 * (size_t)p0 + tid);
+    if (tid + 256 < 9 * np) r_Vi1 = __ldcs(A.Vinv + 9 * (size_t)p0 + tid + 256);
+    if (tid < nob) { r_cam0 = __ldcs(o.obs_cam + ob0 + tid); r_uv0 = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob0 + tid); }
+    if (tid + 256 < nob) { r_cam1 = __ldcs(o.obs_cam + ob0 + tid + 256); r_uv1 = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob0 + tid + 256); }
+  };
+  int c_cur = blockIdx.x;
+  int p0, np, ob0, nob;            // chunk whose data sits in registers
+  bounds(c_cur, p0, np, ob0, nob);
+  int n_p0, n_np, n_ob0, n_nob;    // bounds of the chunk after it
+  bounds(c_cur + gridDim.x, n_p0, n_np, n_ob0, n_nob);
+  fetch(p0, np, ob0, nob);
+
+  // ---- cameras: every CTA retracts all of them itself (see backsub_cost_kernel) -------------
+  for (int i = tid; i < o.n_cam; i += blockDim.x) {
+    double R[9], t[3], Rc[9], tc[3];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) R[j] = o.cam_R[9 * i + j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) t[j] = o.cam_t[3 * i + j];
+    const int slot = o.cam_slot[i];
+    slot_sm[i] = slot;
+    if (slot >= 0) {
+      double d[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const double v = A.dC[6 * slot + j];
+        cam_sm[24 * o.n_cam + 6 * i + j] = v;
+        d[j] = -v;
+      }
+      camera_retract(R, t, d, Rc, tc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) cam_sm[24 * o.n_cam + 6 * i + j] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) Rc[j] = R[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tc[j] = t[j];
+    }
+    double* s0 = cam_sm + 12 * i;
+    double* s1 = cam_sm + 12 * (o.n_cam + i);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { s0[j] = R[j]; s1[j] = Rc[j]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s0[9 + j] = t[j]; s1[9 + j] = tc[j]; }
+    if (blockIdx.x == 0) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) A.cand_R_out[9 * i + j] = Rc[j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) A.cand_t_out[3 * i + j] = tc[j];
+    }
+  }
+
+  double cost_acc = 0.0;
+  for (; c_cur < n_chunks; c_cur += gridDim.x) {
+    __syncthreads();   // the previous chunk's readers are done with the stage (first time round: the cameras are in place)
+    if (tid <= np) S.ptr[tid] = r_ptr;
+    if (tid < np) S.slot[tid] = r_slot;
+    if (tid < 3 * np) { S.x[tid] = r_x; S.bP[tid] = r_bP; }
+    if (tid < 9 * np) S.Vi[tid] = r_Vi0;
+    if (tid + 256 < 9 * np) S.Vi[tid + 256] = r_Vi1;
+    if (tid < nob) { S.cam[tid] = r_cam0; S.uv[tid] = r_uv0; }
+    if (tid + 256 < nob) { S.cam[tid + 256] = r_cam1; S.uv[tid + 256] = r_uv1; }
+    const int c_p0 = p0, c_np = np, c_ob0 = ob0;
+    // next chunk's loads go out now and land while this chunk is computed
+    p0 = n_p0; np = n_np; ob0 = n_ob0; nob = n_nob;
+    bounds(c_cur + 2 * gridDim.x, n_p0, n_np, n_ob0, n_nob);
+    fetch(p0, np, ob0, nob);
+    __syncthreads();
+
+    for (int lp = wid * NG + sub; lp < c_np + (NG - 1 - (c_np + NG - 1) % NG); lp += 8 * NG) {   // whole lane groups take part in the shuffles
+      const bool live = lp < c_np;
+      const int pt = c_p0 + lp;
+      const int beg = live ? S.ptr[lp] - c_ob0 : 0;
+      const int k = live ? S.ptr[lp + 1] - c_ob0 - beg : 0;
+      const int pslot = live ? S.slot[lp] : -1;
+      double x[3] = {0.0, 0.0, 0.0};
+      if (live) { x[0] = S.x[3 * lp]; x[1] = S.x[3 * lp + 1]; x[2] = S.x[3 * lp + 2]; }
+      double xc[3] = {x[0], x[1], x[2]};
+      double acc[3] = {0, 0, 0};
+      if (pslot >= 0) {
+        for (int a = gl; a < k; a += G) {
+          const int cam = S.cam[beg + a];
+          if (slot_sm[cam] < 0) continue;
+          const double2 uv = S.uv[beg + a];
+          double r[2], Jc[12], Jp[6];
+          observe(o.intr, o.model, cam_sm + 12 * cam, cam_sm + 12 * cam + 9, x, uv.x, uv.y, r, Jc, Jp);
+          const double* d = dC_sm + 6 * cam;
+          double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) { q0 += Jc[j] * d[j]; q1 += Jc[6 + j] * d[j]; }
+#pragma unroll
+          for (int m = 0; m < 3; ++m) acc[m] += Jp[m] * q0 + Jp[3 + m] * q1;
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) acc[m] = group_sum<G>(acc[m]);
+      if (pslot >= 0) {
+        const double g0 = S.bP[3 * lp] - acc[0], g1 = S.bP[3 * lp + 1] - acc[1], g2 = S.bP[3 * lp + 2] - acc[2];
+        const double* Vi = S.Vi + 9 * lp;
+        double dp[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dp[m] = Vi[3 * m] * g0 + Vi[3 * m + 1] * g1 + Vi[3 * m + 2] * g2;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) xc[m] = x[m] - dp[m];
+        if (gl == 0) {
+#pragma unroll
+          for (int m = 0; m < 3; ++m) A.dP[3 * (size_t)pt + m] = dp[m];
+        }
+      } else if (live && gl == 0) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) A.dP[3 * (size_t)pt + m] = 0.0;
+      }
+      if (live && gl == 0) {
+#pragma unroll
+        for (int m = 0; m < 3; ++m) A.cand_pts[3 * (size_t)pt + m] = xc[m];
+      }
+      if (pslot >= 0) {
+        for (int a = gl; a < k; a += G) {
+          const int cam = S.cam[beg + a];
+          if (slot_sm[cam] < 0) continue;
+          const double2 uv = S.uv[beg + a];
+          double r[2];
+          residual_only(o.intr, o.model, cam_sm + 12 * (o.n_cam + cam), cam_sm + 12 * (o.n_cam + cam) + 9, xc, uv.x, uv.y, r);
+          cost_acc += r[0] * r[0] + r[1] * r[1];
+        }
+      }
+    }
+  }
+  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+}
+
 // ------------------------------------------------------------------------------------------
 struct CostArgs {
   ObsArgs o;
@@ -1001,8 +1188,13 @@ cudaError_t launch_linearize_eliminate(Context& c, double damping, double rcond,
       if (grid > 2 * c.num_sms) grid = 2 * c.num_sms;
       if (grid < 1) grid = 1;
       if (grid > c.partials_cap) grid = c.partials_cap;
+      A.diag_rep = c.diag_rep;
       gk<<<grid, gw * 32, gsmem, st>>>(A);
       c.launches += 1;
+      if (c.n_opt_cam > 0) {
+        fold_diag_kernel<<<c.n_opt_cam, 64, 0, st>>>(c.sys, c.diag_rep, c.n_opt_cam);
+        c.launches += 1;
+      }
       return cudaGetLastError();
     }
   }
@@ -1069,8 +1261,31 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   // (a software-pipelined single-pass variant at 2 CTAs/SM measured 73 us against 56 us for this
   // one at 3 CTAs/SM: occupancy beats a shorter dependency chain here)
   const int g = kmax <= 12 ? 8 : (kmax <= 24 ? 16 : 32);
-  const int grid = point_grid(c, 8 * (32 / g), 3);
   cudaError_t e = cudaSuccess;
+  // tile-streamed variant: cameras in shared memory and a chunk of >= 8 points within kTileObs observations
+  {
+    static const bool tile_off = getenv("PYSFM_B200_BACKSUB_TILE") && getenv("PYSFM_B200_BACKSUB_TILE")[0] == '0';
+    int P = kTileObs / kmax;
+    if (P > kTilePts) P = kTilePts;
+    P -= P % (32 / g);
+    const size_t tile_smem = (((size_t)31 * c.n_cam + 2) & ~(size_t)1) * sizeof(double) + sizeof(TileStage);
+    if (sc && !tile_off && P >= 8 && tile_smem <= 100 * 1024) {
+      typedef void (*TileKernel)(const BacksubArgs, int);
+      TileKernel tk = g == 8 ? backsub_tile_kernel<8> : (g == 16 ? backsub_tile_kernel<16> : backsub_tile_kernel<32>);
+      bool& attr = c.backsub_tile_attr_set[g == 8 ? 0 : (g == 16 ? 1 : 2)];
+      if (!attr) {
+        if ((e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        attr = true;
+      }
+      const int n_chunks = (c.n_pt + P - 1) / P;
+      int grid = n_chunks < 2 * c.num_sms ? n_chunks : 2 * c.num_sms;
+      if (grid > c.partials_cap) grid = c.partials_cap;
+      tk<<<grid, 256, tile_smem, st>>>(A, P);
+      c.launches += 1;
+      return cudaGetLastError();
+    }
+  }
+  const int grid = point_grid(c, 8 * (32 / g), 3);
 #define BA_LAUNCH_BACKSUB(G)                                                                          \
   do {                                                                                                \
     if (sc) {                                                                                         \

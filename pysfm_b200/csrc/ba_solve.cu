@@ -264,6 +264,8 @@ struct CholArgs {
   unsigned int* __restrict__ abort;   // [1] != 0: some spin-wait (here or on a peer) gave up; every wait falls through
   unsigned long long spin_limit_ns;   // budget of the whole launch for waiting
   int strict;                         // release/acquire publication of the column-block flags (PTX-model clean, slower)
+  int split;                          // 1: diagonal-update tasks D_j carry the W / y part of the chain tasks' k loops (large T);
+                                      // 0: the chain task does it all and D_j is empty (small T: the hand-over costs more than it hides)
   // ---- distributed mode (DIST): tiles are owned by ranks, see the header of the kernel ----
   int world, rank;
   const int* __restrict__ tasks;      // this rank's tasks in global ticket order: (i << 16) | j, chain task C_j as (j, j)
@@ -633,7 +635,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // The diagonal tile A_jj belongs to the diagonal-update task D_j (C_0 has none and loads its own);
     // the chain task starts from W = 0, takes the updates of the last two columns itself and adds
     // D_j's partial tile before its sweep.
-    const bool loadW = diag || (chain && j == 0);
+    const bool split = g.split != 0;
+    if (diag && !split) {   // nothing to hand over: the chain task keeps its whole k loop
+      BA_TRACE(t, 3);
+      BA_TRACE(t, 5);
+      continue;
+    }
+    const bool wk = diag || (chain && !split);      // this task's k loop updates W and the forward-substitution sum
+    const bool loadW = diag || (chain && (j == 0 || !split));
     if (!DIST && loadW) {
       const double* Ajj = g.A + (size_t)(j * NB) * ld + (size_t)j * NB;
 #pragma unroll
@@ -683,7 +692,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     auto wait_k = [&](int k) {
       wait_flag<DIST>(g, &g.flags[(size_t)pi * T + k], epoch, s_t0);
       if (!diag) wait_flag<DIST>(g, &g.flags[(size_t)pj * T + k], epoch, s_t0);
-      if (diag) wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
+      if (wk) wait_flag<DIST>(g, &yflag[k], epoch, s_t0);
     };
     // The tiles of step k+1 are prefetched while step k computes ONLY if they are already
     // published; otherwise step k runs first and the wait comes after it.  (Blocking on the flags
@@ -714,7 +723,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
             if (lane < 8 && kk < kfull) {
               const unsigned int f0 = ldf_relaxed<DIST>(&g.flags[(size_t)pi * T + kk]);
               const unsigned int f1 = diag ? epoch : ldf_relaxed<DIST>(&g.flags[(size_t)pj * T + kk]);
-              const unsigned int f2 = diag ? ldf_relaxed<DIST>(&yflag[kk]) : epoch;
+              const unsigned int f2 = wk ? ldf_relaxed<DIST>(&yflag[kk]) : epoch;
               ok = f0 == epoch && f1 == epoch && f2 == epoch;
             }
             const unsigned int mask = __ballot_sync(0xffffffffu, ok) & 0xffu;
@@ -738,11 +747,11 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       } else {
         cp_async_wait<0>();
       }
-      if (diag && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
+      if (wk && tid < NB) yk[tid] = __ldcg(g.rhs + k * NB + tid);  // y_k
       __syncthreads();
       const double* P = buf + (size_t)(2 * (k & 1)) * kTileDoubles;
       if (!diag) tile_dmma<true>(acc, P, P + kTileDoubles, R0, C0, lane);
-      if (diag) {
+      if (wk) {
         diag_rows_dmma(W, P, r, lane);
         if (tid < NB) {
           double s = 0.0;
@@ -877,7 +886,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     BA_TRACE(t, 3);   // k loop done
     double* const Ws = buf + 3 * kTileDoubles;   // chain: D_j's partial diagonal tile, [col*LDT + row]
     double vpart = 0.0;
-    if (chain && j > 0) {
+    if (chain && j > 0 && split) {
       // D_j was grabbed right before this task and has less to do: its partial tile is (all but
       // always) there by now.  It is staged into the one operand buffer the panel phase leaves
       // alone and added to W after the fold, so the L2 latency hides behind the panel phase.
@@ -1114,7 +1123,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // tile (pi, pj) of L is complete.  The last group was stored directly; warp 1 releases it
       // (warp 0 starts the sweep of a chain task, warp 7 has the most of W left to fold; the
       // fence stalls global traffic only, and the rest of a chain task works out of shared memory).
-      if (chain) cp_async_wait<0>();   // D_j's partial tile (Ws)
+      if (chain && split) cp_async_wait<0>();   // D_j's partial tile (Ws)
       __syncthreads();
       if (wid == 1) {
         if (lane >= last_cb && lane < 8) st_release(colflag + ((size_t)pi * T + pj) * 8 + lane, epoch);
@@ -1130,7 +1139,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       // critical path of the factorisation.
       if (DIST && !chain) push_tile_to_peers();
       if (chain && ub < 8) fold(ub, 8);
-      if (chain) {   // (a chain task with a panel has j > 0)
+      if (chain && split) {   // (a chain task with a panel has j > 0)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -1630,6 +1639,7 @@ static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st
   g.abort = reinterpret_cast<unsigned int*>(base + dl.abort);
   g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
   g.prof = c.solve_prof_on ? c.solve_prof : nullptr;
+  g.split = T >= c.split_min_tiles;
   g.strict = c.strict_flags;
   g.world = c.comm_world; g.rank = c.comm_rank;
   g.tasks = c.dist_tasks; g.ntasks = c.dist_ntasks;
@@ -1674,6 +1684,7 @@ cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   g.abort = c.solve_abort;
   g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
   g.prof = c.solve_prof_on ? c.solve_prof : nullptr;
+  g.split = T >= c.split_min_tiles;
   g.strict = c.strict_flags;
   g.world = 1; g.rank = 0;
 #ifdef BA_SOLVE_TRACE
