@@ -302,6 +302,23 @@ __device__ __forceinline__ void wait_flag(const CholArgs& g, const unsigned int*
                                           int site = kProfWaitK) {
   if (threadIdx.x == 0) {
     unsigned int spins = 0;
+    if (SYS) {
+      // Distributed solve: an acquire load at system scope is a load plus MEMBAR.SYS, and that fence
+      // waits for every store this thread's SM has on the links (the tile it just pushed to seven
+      // peers): a loaded NVLink round trip PER POLL.  The polls are relaxed; what the flag guards is
+      // read from L2 (cp.async.cg / ld.cg) after the flag load returned, L2 being the point of
+      // coherence for this GPU's memory whoever wrote it; g.strict adds the fence.
+      if (ld_relaxed_sys(f) != epoch) {
+        BA_PROF_T0();
+        while (ld_relaxed_sys(f) != epoch) {
+          if (spin_expired(g, spins, t0)) break;
+          __nanosleep(20);
+        }
+        BA_PROF_ADD(site);
+      }
+      if (g.strict) __threadfence_system();
+      return;
+    }
     if (ldf_acquire<SYS>(f) == epoch) return;
     BA_PROF_T0();
     while (ldf_acquire<SYS>(f) != epoch) {
@@ -1485,7 +1502,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
     wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0, kProfBackward);   // L_kk^{-1}
     wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0, kProfBackward);                        // y_k
-    for (int i = T - 1; i > k; --i) wait_flag<DIST>(g, &g.flags[(size_t)i * T + k], epoch, s_t0, kProfBackward);   // tiles (i, k)
+    // tiles (i, k), i > k: one flag per thread, polled side by side (a single thread walking down a
+    // column of 188 flags is 188 dependent L2 round trips in front of every task)
+    for (int i0 = T - 1; i0 > k; i0 -= kSolveThreads) {
+      const int i = i0 - tid;
+      if (i > k) {
+        const unsigned int* f = &g.flags[(size_t)i * T + k];
+        unsigned int spins = 0;
+        while (ldf_relaxed<DIST>(f) != epoch) {
+          if (spin_expired(g, spins, s_t0)) break;
+          __nanosleep(40);
+        }
+      }
+    }
+    if (!DIST) __threadfence(); else if (g.strict) __threadfence_system();   // acquire for the tiles (read with ld.cg below)
     __syncthreads();
     {
       const double* LT = g.LinvT + (size_t)k * NB * NB;
