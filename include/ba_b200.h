@@ -73,7 +73,10 @@ enum {
                                       (default 32, i.e. >= 2048 camera parameters; 0 = never) */
   BA_OPT_DIST_BAND = 3,            /* distributed solve: tiles with i - j <= band stay on rank 0 */
   BA_OPT_SOLVE_GRID_CAP = 4,       /* at most this many solver CTAs (0 = one per SM) */
-  BA_OPT_SOLVER_PROFILE = 5        /* 1: the solver accumulates its wait-time profile (ba_solver_profile) */
+  BA_OPT_SOLVER_PROFILE = 5,       /* 1: the solver accumulates its wait-time profile (ba_solver_profile) */
+  BA_OPT_FUSE_COST_REDUCTION = 6   /* sharded handles over peer memory (default 1): ba_backsub_retract_cost reduces
+                                      {cost, candidate cost} over the ranks in its own epilogue and the following
+                                      ba_allreduce_costs is a no-op; set the same value on every rank */
 };
 
 enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */
@@ -201,7 +204,8 @@ int ba_scalars_ptr(ba_handle h, double** scalars_dev);
  *   ba_allreduce_system  ONE kernel: barrier, each rank sums its slice of all ranks' packed systems
  *                     (rank order) and pushes it to every rank, barrier; the next ba_solve factors
  *                     the reduced copy.  Replaces the NCCL all-reduce of the reduced camera system;
- *   ba_allreduce_costs   sums {cost, candidate cost} over the ranks into every rank's scalars.
+ *   ba_allreduce_costs   sums {cost, candidate cost} over the ranks into every rank's scalars (a no-op
+ *                     right after a ba_backsub_retract_cost that already did it, BA_OPT_FUSE_COST_REDUCTION).
  * All ranks must issue the same sequence of these two calls. */
 int ba_comm_create(ba_handle h, int rank, int world, unsigned char* ipc_handle_out64);
 int ba_comm_connect(ba_handle h, const unsigned char* ipc_handles_all);

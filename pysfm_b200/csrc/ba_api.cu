@@ -242,6 +242,10 @@ int ba_allreduce_system(ba_handle h, void* stream) {
 int ba_allreduce_costs(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!h->comm_buf) return BA_ERR_NOT_BOUND;
+  if (h->costs_reduced) {      // ba_backsub_retract_cost already reduced them in its epilogue
+    h->costs_reduced = false;
+    return BA_OK;
+  }
   BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_peer_allreduce_costs(*h, (cudaStream_t)stream));
   return BA_OK;
@@ -327,6 +331,7 @@ int ba_set_option(ba_handle h, int option, double value) {
       break;
     case BA_OPT_SOLVE_GRID_CAP: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->solve_grid_cap = (int)value; break;
     case BA_OPT_SOLVER_PROFILE: h->solve_prof_on = value != 0.0; break;
+    case BA_OPT_FUSE_COST_REDUCTION: h->fuse_cost_reduction = value != 0.0; break;
     default: return BA_ERR_BAD_ARGUMENT;
   }
   return BA_OK;
@@ -350,6 +355,7 @@ int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int f
   if (rc != BA_OK) return rc;
   if ((flags & BA_WANT_BLOCKS) && !h->W) BA_CUDA(h, dev_alloc(&h->W, (size_t)h->n_obs * 18));
   if (flags & BA_WANT_SCHUR) h->sys_state = ba::kSysLocal;   // a fresh local contribution
+  h->costs_reduced = false;                                   // ... and a fresh local cost
   cudaError_t e = ba::launch_linearize_eliminate(*h, damping, pinv_rcond, flags, st);
   BA_CUDA(h, e);
   return BA_OK;
@@ -377,6 +383,7 @@ int ba_backsub_retract_cost(ba_handle h, void* stream) {
 int ba_cost(ba_handle h, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h)) return BA_ERR_NOT_BOUND;
+  h->costs_reduced = false;
   BA_ON_DEVICE(h);
   BA_CUDA(h, ba::launch_cost(*h, (cudaStream_t)stream));
   return BA_OK;

@@ -130,6 +130,8 @@ struct Context {
   double* comm_peer[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned int* comm_done = nullptr;        // last-CTA-done counter of the all-reduce kernel
   unsigned int comm_epoch = 0;
+  bool fuse_cost_reduction = true;          // BA_OPT_FUSE_COST_REDUCTION: backsub's last CTA also reduces the costs over the ranks
+  bool costs_reduced = false;               // the scalars already hold the sums over all ranks
   int sys_state = kSysLocal;                // what the bound system holds (which copy the solver reads)
   // distributed reduced solve (tiles owned by ranks, operands exchanged over peer memory)
   size_t dist_off = 0;                      // doubles from comm_buf to the rank's DistLayout section (0 = none)

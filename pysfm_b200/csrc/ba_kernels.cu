@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "ba_context.h"
+#include "ba_peer.cuh"
 
 namespace ba {
 
@@ -41,11 +42,14 @@ struct ObsArgs {
   const double* __restrict__ pts;
 };
 
-// Deterministic grid-wide sum: every CTA deposits one partial, the last CTA to arrive adds
-// them in index order and stores the total.  `ticket` must be zero on entry and is reset.
-__device__ __forceinline__ void grid_sum_store(double warp_total, double* __restrict__ partials,
-                                               unsigned int* __restrict__ ticket,
-                                               double* __restrict__ out) {
+// Deterministic grid-wide sum: every CTA deposits one partial; the last CTA to arrive adds them up
+// -- all its threads load (one thread walking a few hundred partials with dependent volatile loads
+// was ~20 us at the end of every kernel that carries a cost), each thread its strided share in index
+// order, then a fixed shuffle tree and the warps in order: the result depends on the grid size only,
+// never on timing -- and returns the total to its thread 0 (other CTAs / threads: 0, last == false).
+// `ticket` must be zero on entry and is reset.
+__device__ __forceinline__ double grid_sum(double warp_total, double* __restrict__ partials,
+                                           unsigned int* __restrict__ ticket, bool& last) {
   __shared__ double s_warp[32];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -60,12 +64,61 @@ __device__ __forceinline__ void grid_sum_store(double warp_total, double* __rest
     s_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) t += ((volatile double*)partials)[i];
-    *out = t;
+  last = s_last;
+  if (!s_last) return 0.0;
+  __threadfence();
+  double v = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(partials + i);
+  v = warp_sum(v);
+  __syncthreads();            // (everybody has read s_warp's first use)
+  if (lane == 0) s_warp[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nw; ++i) t += s_warp[i];
     *ticket = 0u;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void grid_sum_store(double warp_total, double* __restrict__ partials,
+                                               unsigned int* __restrict__ ticket,
+                                               double* __restrict__ out) {
+  bool last;
+  const double t = grid_sum(warp_total, partials, ticket, last);
+  if (last && threadIdx.x == 0) *out = t;
+}
+
+// grid_sum_store for the candidate cost of a SHARDED problem: the last CTA of the rank also does the
+// cross-rank reduction of {cost, candidate cost} over peer memory -- push both partial sums into
+// every rank's bank, flag, wait for everybody's, add in rank order -- which used to be a launch
+// (peer_allreduce_costs_kernel) and a barrier of its own after every back-substitution.
+__device__ __forceinline__ void grid_sum_store_peer(double warp_total, double* __restrict__ partials,
+                                                    unsigned int* __restrict__ ticket, Scalars* __restrict__ sc,
+                                                    const PeerArgs& g) {
+  __shared__ double s_total;
+  bool last;
+  const double total = grid_sum(warp_total, partials, ticket, last);
+  if (!last) return;
+  if (threadIdx.x == 0) s_total = total;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int tid = threadIdx.x;
+    const int bank = (int)(g.epoch & 1u) * 2 * kMaxPeers;
+    if (tid < g.world) {
+      double* c = costs_of(g.base[tid], g.sys_len) + bank + 2 * g.rank;
+      c[0] = sc->cost;
+      c[1] = s_total;
+    }
+    peer_barrier(g, 2, tid);
+    __syncwarp();
+    if (tid == 0) {
+      const volatile double* c = costs_of(g.base[g.rank], g.sys_len) + bank;
+      double a = 0.0, b = 0.0;
+      for (int p = 0; p < g.world; ++p) { a += c[2 * p]; b += c[2 * p + 1]; }
+      sc->cost = a;
+      sc->cand_cost = b;
+    }
   }
 }
 
@@ -659,7 +712,14 @@ struct BacksubArgs {
   double* __restrict__ partials;
   unsigned int* __restrict__ ticket;
   double* __restrict__ cost_out;
+  Scalars* sc;               // the handle's scalar record (cost_out == &sc->cand_cost)
+  PeerArgs peer;             // peer.world > 1: the cost reduction over the ranks is fused into the kernel's epilogue
 };
+
+__device__ __forceinline__ void backsub_cost_epilogue(double warp_total, const BacksubArgs& A) {
+  if (A.peer.world > 1) grid_sum_store_peer(warp_total, A.partials, A.ticket, A.sc, A.peer);
+  else grid_sum_store(warp_total, A.partials, A.ticket, A.cost_out);
+}
 
 // sum over the G-lane group a lane belongs to (G = 8, 16 or 32, groups are lane-aligned)
 template <int G>
@@ -811,36 +871,42 @@ __global__ void __launch_bounds__(256, 3) backsub_cost_kernel(const BacksubArgs 
       }
     }
   }
-  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+  backsub_cost_epilogue(warp_sum(cost_acc), A);
 }
 
 
 // ------------------------------------------------------------------------------------------
-// Back-substitution, TILE-STREAMED (the default whenever the cameras fit in shared memory and no
-// track is longer than 64 views).  backsub_cost_kernel above walks a dependent chain of global
-// loads per point (pt_ptr -> obs_cam -> slot -> obs_uv -> Vinv / bP) and ran at 6.6 % of the HBM
-// peak.  Here a CTA owns CHUNKS of kTilePts consecutive points: the point-major CSR makes every
-// array of a chunk one contiguous range, so the whole chunk -- CSR offsets, points, slots, Vinv,
-// bP and up to kTileObs observation records -- is fetched with independent, coalesced loads into
-// registers while the PREVIOUS chunk is being computed out of shared memory, and parked in shared
-// memory at the top of the next iteration (the bounds of the chunk after next travel one iteration
-// further ahead).  All arithmetic then reads shared memory only; the results (dP, candidate point)
-// are the only global stores.  Cameras, their candidate poses, dC and slots live in shared memory
-// as in the SC variant above.
+// Back-substitution, TILE-STREAMED and OBSERVATION-PARALLEL (the default whenever the cameras fit in
+// shared memory and no track is longer than 64 views).  backsub_cost_kernel above walks a dependent
+// chain of global loads per point (pt_ptr -> obs_cam -> slot -> obs_uv -> Vinv / bP) with 10 of 16
+// lanes busy at 10 observations per point, and ran at 6.6 % of the HBM peak.  Here a CTA owns
+// CHUNKS of P consecutive points holding at most kTileObs = 256 observations (one per thread):
+//   * the point-major CSR makes every array of a chunk one contiguous range, so the whole chunk --
+//     CSR offsets, points, slots, Vinv, bP and the observation records -- is fetched with
+//     independent, coalesced loads into registers while the PREVIOUS chunk is being computed, and
+//     parked in shared memory at the top of the next iteration (the bounds of the chunk after next
+//     travel one iteration further ahead);
+//   * pass 1, thread = observation: Jacobians at the linearisation point, Jp^T (Jc dC) into shared
+//     memory;  pass 2, thread = point: sum of the point's terms in observation order (no atomics:
+//     deterministic), dP = Vinv (bP - sum), candidate point;  pass 3, thread = observation: residual
+//     of the candidate.  All 256 lanes work in the two expensive passes.
+// Cameras, their candidate poses, dC and slots live in shared memory as in the SC variant above.
 constexpr int kTilePts = 32;
-constexpr int kTileObs = 512;
+constexpr int kTileObs = 256;
 
 struct TileStage {     // shared-memory image of one chunk
   int ptr[kTilePts + 1];
   int slot[kTilePts];
   double x[3 * kTilePts];
+  double xc[3 * kTilePts];
   double Vi[9 * kTilePts];
   double bP[3 * kTilePts];
   int cam[kTileObs];
   double2 uv[kTileObs];
+  double c[3 * kTileObs];          // pass 1 -> pass 2: Jp^T (Jc dC) of every observation
+  unsigned char pt_of[kTileObs];   // point (position in the chunk) of every observation
 };
 
-template <int G>
 __global__ void __launch_bounds__(256, 2) backsub_tile_kernel(const BacksubArgs A, int P) {
   extern __shared__ __align__(16) double cam_sm[];   // cameras as in backsub_cost_kernel<G, true>, then the stage
   const ObsArgs& o = A.o;
@@ -848,12 +914,9 @@ __global__ void __launch_bounds__(256, 2) backsub_tile_kernel(const BacksubArgs 
   int* const slot_sm = reinterpret_cast<int*>(cam_sm + 30 * o.n_cam);
   TileStage& S = *reinterpret_cast<TileStage*>(cam_sm + ((31 * o.n_cam + 2) & ~1));
   const int tid = threadIdx.x;
-  const int lane = tid & 31, wid = tid >> 5;
-  constexpr int NG = 32 / G;
-  const int sub = lane / G, gl = lane % G;
   const int n_chunks = (o.n_pt + P - 1) / P;
 
-  // ---- chunk pipeline, part 1: bounds two chunks ahead, data one chunk ahead (registers) ----
+  // ---- chunk pipeline: bounds two chunks ahead, data one chunk ahead (registers) -------------
   auto bounds = [&](int c, int& p0, int& np, int& ob0, int& nob) {
     p0 = c * P;
     np = 0; ob0 = 0; nob = 0;
@@ -863,17 +926,16 @@ __global__ void __launch_bounds__(256, 2) backsub_tile_kernel(const BacksubArgs 
       nob = __ldg(o.pt_ptr + p0 + np) - ob0;
     }
   };
-  int r_ptr = 0, r_slot = -1, r_cam0 = 0, r_cam1 = 0;
+  int r_ptr = 0, r_slot = -1, r_cam = 0;
   double r_x = 0.0, r_Vi0 = 0.0, r_Vi1 = 0.0, r_bP = 0.0;
-  double2 r_uv0 = make_double2(0.0, 0.0), r_uv1 = make_double2(0.0, 0.0);
+  double2 r_uv = make_double2(0.0, 0.0);
   auto fetch = [&](int p0, int np, int ob0, int nob) {   // independent loads of one chunk, this thread's share
     if (np > 0 && tid <= np) r_ptr = __ldcs(o.pt_ptr + p0 + tid);   // (np == 0: past the last chunk, nothing to fetch)
     if (tid < np) r_slot = __ldcs(o.pt_slot + p0 + tid);
     if (tid < 3 * np) { r_x = __ldcs(o.pts + 3 * (size_t)p0 + tid); r_bP = __ldcs(A.bP + 3 * (size_t)p0 + tid); }
     if (tid < 9 * np) r_Vi0 = __ldcs(A.Vinv + 9 * (size_t)p0 + tid);
     if (tid + 256 < 9 * np) r_Vi1 = __ldcs(A.Vinv + 9 * (size_t)p0 + tid + 256);
-    if (tid < nob) { r_cam0 = __ldcs(o.obs_cam + ob0 + tid); r_uv0 = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob0 + tid); }
-    if (tid + 256 < nob) { r_cam1 = __ldcs(o.obs_cam + ob0 + tid + 256); r_uv1 = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob0 + tid + 256); }
+    if (tid < nob) { r_cam = __ldcs(o.obs_cam + ob0 + tid); r_uv = __ldcs(reinterpret_cast<const double2*>(o.obs_uv) + ob0 + tid); }
   };
   int c_cur = blockIdx.x;
   int p0, np, ob0, nob;            // chunk whose data sits in registers
@@ -930,75 +992,70 @@ __global__ void __launch_bounds__(256, 2) backsub_tile_kernel(const BacksubArgs 
     if (tid < 3 * np) { S.x[tid] = r_x; S.bP[tid] = r_bP; }
     if (tid < 9 * np) S.Vi[tid] = r_Vi0;
     if (tid + 256 < 9 * np) S.Vi[tid + 256] = r_Vi1;
-    if (tid < nob) { S.cam[tid] = r_cam0; S.uv[tid] = r_uv0; }
-    if (tid + 256 < nob) { S.cam[tid + 256] = r_cam1; S.uv[tid + 256] = r_uv1; }
-    const int c_p0 = p0, c_np = np, c_ob0 = ob0;
+    if (tid < nob) { S.cam[tid] = r_cam; S.uv[tid] = r_uv; }
+    const int c_p0 = p0, c_np = np, c_ob0 = ob0, c_nob = nob;
     // next chunk's loads go out now and land while this chunk is computed
     p0 = n_p0; np = n_np; ob0 = n_ob0; nob = n_nob;
     bounds(c_cur + 2 * gridDim.x, n_p0, n_np, n_ob0, n_nob);
     fetch(p0, np, ob0, nob);
     __syncthreads();
+    if (tid < c_np)    // the point of every observation (tracks are short: a few stores per point)
+      for (int a = S.ptr[tid] - c_ob0, e = S.ptr[tid + 1] - c_ob0; a < e; ++a) S.pt_of[a] = (unsigned char)tid;
+    __syncthreads();
 
-    for (int lp = wid * NG + sub; lp < c_np + (NG - 1 - (c_np + NG - 1) % NG); lp += 8 * NG) {   // whole lane groups take part in the shuffles
-      const bool live = lp < c_np;
-      const int pt = c_p0 + lp;
-      const int beg = live ? S.ptr[lp] - c_ob0 : 0;
-      const int k = live ? S.ptr[lp + 1] - c_ob0 - beg : 0;
-      const int pslot = live ? S.slot[lp] : -1;
-      double x[3] = {0.0, 0.0, 0.0};
-      if (live) { x[0] = S.x[3 * lp]; x[1] = S.x[3 * lp + 1]; x[2] = S.x[3 * lp + 2]; }
-      double xc[3] = {x[0], x[1], x[2]};
-      double acc[3] = {0, 0, 0};
-      if (pslot >= 0) {
-        for (int a = gl; a < k; a += G) {
-          const int cam = S.cam[beg + a];
-          if (slot_sm[cam] < 0) continue;
-          const double2 uv = S.uv[beg + a];
-          double r[2], Jc[12], Jp[6];
-          observe(o.intr, o.model, cam_sm + 12 * cam, cam_sm + 12 * cam + 9, x, uv.x, uv.y, r, Jc, Jp);
-          const double* d = dC_sm + 6 * cam;
-          double q0 = 0.0, q1 = 0.0;
+    // ---- pass 1: thread = observation ------------------------------------------------------
+    int lp = 0, cam = 0;
+    bool use = false;
+    double2 uv = make_double2(0.0, 0.0);
+    if (tid < c_nob) {
+      lp = S.pt_of[tid];
+      cam = S.cam[tid];
+      uv = S.uv[tid];
+      use = S.slot[lp] >= 0 && slot_sm[cam] >= 0;
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      if (use) {
+        const double x[3] = {S.x[3 * lp], S.x[3 * lp + 1], S.x[3 * lp + 2]};
+        double r[2], Jc[12], Jp[6];
+        observe(o.intr, o.model, cam_sm + 12 * cam, cam_sm + 12 * cam + 9, x, uv.x, uv.y, r, Jc, Jp);
+        const double* d = dC_sm + 6 * cam;
+        double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) { q0 += Jc[j] * d[j]; q1 += Jc[6 + j] * d[j]; }
-#pragma unroll
-          for (int m = 0; m < 3; ++m) acc[m] += Jp[m] * q0 + Jp[3 + m] * q1;
-        }
+        for (int j = 0; j < 6; ++j) { q0 += Jc[j] * d[j]; q1 += Jc[6 + j] * d[j]; }
+        c0 = Jp[0] * q0 + Jp[3] * q1;
+        c1 = Jp[1] * q0 + Jp[4] * q1;
+        c2 = Jp[2] * q0 + Jp[5] * q1;
       }
-#pragma unroll
-      for (int m = 0; m < 3; ++m) acc[m] = group_sum<G>(acc[m]);
-      if (pslot >= 0) {
-        const double g0 = S.bP[3 * lp] - acc[0], g1 = S.bP[3 * lp + 1] - acc[1], g2 = S.bP[3 * lp + 2] - acc[2];
-        const double* Vi = S.Vi + 9 * lp;
-        double dp[3];
-#pragma unroll
-        for (int m = 0; m < 3; ++m) dp[m] = Vi[3 * m] * g0 + Vi[3 * m + 1] * g1 + Vi[3 * m + 2] * g2;
-#pragma unroll
-        for (int m = 0; m < 3; ++m) xc[m] = x[m] - dp[m];
-        if (gl == 0) {
-#pragma unroll
-          for (int m = 0; m < 3; ++m) A.dP[3 * (size_t)pt + m] = dp[m];
-        }
-      } else if (live && gl == 0) {
-#pragma unroll
-        for (int m = 0; m < 3; ++m) A.dP[3 * (size_t)pt + m] = 0.0;
+      S.c[3 * tid] = c0; S.c[3 * tid + 1] = c1; S.c[3 * tid + 2] = c2;
+    }
+    __syncthreads();
+    // ---- pass 2: thread = point ---------------------------------------------------------------
+    if (tid < c_np) {
+      const int pt = c_p0 + tid;
+      const double x0 = S.x[3 * tid], x1 = S.x[3 * tid + 1], x2 = S.x[3 * tid + 2];
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+      if (S.slot[tid] >= 0) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int a = S.ptr[tid] - c_ob0, e = S.ptr[tid + 1] - c_ob0; a < e; ++a) { a0 += S.c[3 * a]; a1 += S.c[3 * a + 1]; a2 += S.c[3 * a + 2]; }
+        const double g0 = S.bP[3 * tid] - a0, g1 = S.bP[3 * tid + 1] - a1, g2 = S.bP[3 * tid + 2] - a2;
+        const double* Vi = S.Vi + 9 * tid;
+        d0 = Vi[0] * g0 + Vi[1] * g1 + Vi[2] * g2;
+        d1 = Vi[3] * g0 + Vi[4] * g1 + Vi[5] * g2;
+        d2 = Vi[6] * g0 + Vi[7] * g1 + Vi[8] * g2;
       }
-      if (live && gl == 0) {
-#pragma unroll
-        for (int m = 0; m < 3; ++m) A.cand_pts[3 * (size_t)pt + m] = xc[m];
-      }
-      if (pslot >= 0) {
-        for (int a = gl; a < k; a += G) {
-          const int cam = S.cam[beg + a];
-          if (slot_sm[cam] < 0) continue;
-          const double2 uv = S.uv[beg + a];
-          double r[2];
-          residual_only(o.intr, o.model, cam_sm + 12 * (o.n_cam + cam), cam_sm + 12 * (o.n_cam + cam) + 9, xc, uv.x, uv.y, r);
-          cost_acc += r[0] * r[0] + r[1] * r[1];
-        }
-      }
+      S.xc[3 * tid] = x0 - d0; S.xc[3 * tid + 1] = x1 - d1; S.xc[3 * tid + 2] = x2 - d2;
+      A.dP[3 * (size_t)pt] = d0; A.dP[3 * (size_t)pt + 1] = d1; A.dP[3 * (size_t)pt + 2] = d2;
+      A.cand_pts[3 * (size_t)pt] = x0 - d0; A.cand_pts[3 * (size_t)pt + 1] = x1 - d1; A.cand_pts[3 * (size_t)pt + 2] = x2 - d2;
+    }
+    __syncthreads();
+    // ---- pass 3: thread = observation, residual of the candidate -----------------------------
+    if (use) {
+      const double xc[3] = {S.xc[3 * lp], S.xc[3 * lp + 1], S.xc[3 * lp + 2]};
+      double r[2];
+      residual_only(o.intr, o.model, cam_sm + 12 * (o.n_cam + cam), cam_sm + 12 * (o.n_cam + cam) + 9, xc, uv.x, uv.y, r);
+      cost_acc += r[0] * r[0] + r[1] * r[1];
     }
   }
-  grid_sum_store(warp_sum(cost_acc), A.partials, A.ticket, A.cost_out);
+  backsub_cost_epilogue(warp_sum(cost_acc), A);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1254,6 +1311,17 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   A.cand_R_out = c.cand.cam_R; A.cand_t_out = c.cand.cam_t;
   A.dC = c.dC; A.Vinv = c.Vinv; A.bP = c.bP; A.dP = c.dP;
   A.partials = c.partials; A.ticket = c.counters + 1; A.cost_out = &c.scalars->cand_cost;
+  A.sc = c.scalars;
+  A.peer.world = 0;
+  c.costs_reduced = false;
+  if (c.fuse_cost_reduction && c.comm_buf && c.comm_world > 1) {
+    bool connected = true;
+    for (int p = 0; p < c.comm_world; ++p) connected = connected && c.comm_peer[p] != nullptr;
+    if (connected) {
+      A.peer = make_peer_args(c);       // (one epoch of the handle's collectives, like ba_allreduce_costs)
+      c.costs_reduced = true;           // ba_allreduce_costs has nothing left to do for this trial
+    }
+  }
   // lanes per point: the narrowest group that holds the longest track in at most two passes
   // (a group of 8 with two lanes doing a second observation beats a group of 16 with six idle
   // lanes at 10 observations per point: 46 -> 43 us -- the kernel is bound by loads in flight)
@@ -1262,25 +1330,22 @@ cudaError_t launch_backsub_retract_cost(Context& c, cudaStream_t st) {
   // one at 3 CTAs/SM: occupancy beats a shorter dependency chain here)
   const int g = kmax <= 12 ? 8 : (kmax <= 24 ? 16 : 32);
   cudaError_t e = cudaSuccess;
-  // tile-streamed variant: cameras in shared memory and a chunk of >= 8 points within kTileObs observations
+  // tile-streamed, observation-parallel variant: cameras in shared memory and chunks of >= 4 points
+  // within kTileObs observations (one per thread)
   {
     static const bool tile_off = getenv("PYSFM_B200_BACKSUB_TILE") && getenv("PYSFM_B200_BACKSUB_TILE")[0] == '0';
     int P = kTileObs / kmax;
     if (P > kTilePts) P = kTilePts;
-    P -= P % (32 / g);
     const size_t tile_smem = (((size_t)31 * c.n_cam + 2) & ~(size_t)1) * sizeof(double) + sizeof(TileStage);
-    if (sc && !tile_off && P >= 8 && tile_smem <= 100 * 1024) {
-      typedef void (*TileKernel)(const BacksubArgs, int);
-      TileKernel tk = g == 8 ? backsub_tile_kernel<8> : (g == 16 ? backsub_tile_kernel<16> : backsub_tile_kernel<32>);
-      bool& attr = c.backsub_tile_attr_set[g == 8 ? 0 : (g == 16 ? 1 : 2)];
-      if (!attr) {
-        if ((e = cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-        attr = true;
+    if (sc && !tile_off && P >= 4 && c.max_track_len >= 1 && tile_smem <= 100 * 1024) {
+      if (!c.backsub_tile_attr_set[0]) {
+        if ((e = cudaFuncSetAttribute(backsub_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+        c.backsub_tile_attr_set[0] = true;
       }
       const int n_chunks = (c.n_pt + P - 1) / P;
       int grid = n_chunks < 2 * c.num_sms ? n_chunks : 2 * c.num_sms;
       if (grid > c.partials_cap) grid = c.partials_cap;
-      tk<<<grid, 256, tile_smem, st>>>(A, P);
+      backsub_tile_kernel<<<grid, 256, tile_smem, st>>>(A, P);
       c.launches += 1;
       return cudaGetLastError();
     }
