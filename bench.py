@@ -10,9 +10,15 @@ candidate cost), the accept path of bundle_adjuster.py:127-157.
 
 Workload: BASELINE config 2 (200 cameras / 50,000 points / 500,000 observations, sigma = 1 px)
 per GPU.  With N > 1 ranks the scene has N x 50,000 points over the same 200 cameras (weak
-scaling), points sharded contiguously, the reduced camera system all-reduced over NCCL once
-per step plus an 16-byte cost reduction (ba_comm.cu peer-memory kernels on one node;
-PYSFM_B200_COLLECTIVE=nccl selects the torch.distributed all-reduce instead).
+scaling), points sharded contiguously, the reduced camera system all-reduced once per step and
+the two costs reduced in the back-substitution's epilogue (ba_comm.cu / ba_kernels.cu kernels over
+CUDA-IPC peer memory on one node; PYSFM_B200_COLLECTIVE=nccl selects torch.distributed instead).
+
+The line also carries `c4`: BASELINE config 4 (2,000 cameras / 1 M points / 10 M observations) as a
+STRONG-scaling run on the same N ranks (points sharded, distributed reduced solve for N > 1), with
+its own stage times and a parity block against the oracle's step (tests/golden/config4_step.npz);
+`--no-c4` skips it.  `parity` = this run's costs / updates against the oracle on the same scene;
+the process exits non-zero when any parity figure exceeds 1e-6.
 
 Keys of the JSON line: see the builder contract.  `value` = device-timed throughput with the
 scene resident in HBM; `e2e` = the same iteration driven from HOST buffers (pinned), H2D of
@@ -495,16 +501,17 @@ def run_ours(args):
         # why the traffic is BELOW the algorithmic bytes for the first two).
         #   linearize_eliminate: 20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24) + packed S + rhs + cameras
         #   chol_dataflow:       packed system read once + dense factor written once and read once by the substitutions
-        #   backsub_cost:        20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24, dP 24, x' 24)
+        #   backsub_tile:        20 B/obs record + per point (pt_ptr 8, x 24, Vinv 72, bP 24, dP 24, x' 24)
         elim_bytes = 20 * n_obs_local + 128 * n_pt_local + 8 * (n * (n + 1) // 2 + n) + 96 * n_cam
         solve_bytes = 8 * (n * (n + 1) // 2 + n) + 2 * 8 * (ld_sys * (ld_sys + 1) // 2)
         back_bytes = 20 * n_obs_local + 176 * n_pt_local + 96 * n_cam
         traffic, traffic_src = ncu_traffic() if world == 1 else ({}, None)
         kern = [("linearize_eliminate_kernel", elim_bytes, stage_ms["linearize_eliminate"],
-                 "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.75e11 adds/s = 0.172 ms"),
+                 "L2 FP64 reduction rate: 36*sum k(k+1)/2 + 6*obs = 1.0e8 adds at the measured 5.7e11 adds/s (uniformly spread blocks) = 0.179 ms"),
                 ("chol_dataflow_kernel", solve_bytes, stage_ms["solve"],
                  "one SM's FP64 rate per tile column (sweep of the diagonal tile + the next chain task's panel phase: ~12.5 us x T columns), not bytes or chip flops"),
-                ("backsub_cost_kernel", back_bytes, stage_ms["backsub_retract_cost"], "HBM latency / occupancy")]
+                ("backsub_tile_kernel", back_bytes, stage_ms["backsub_retract_cost"],
+                 "FP64 issue (~300 dependent DP instructions per observation, ~10 us) + per-chunk barriers and the camera prologue")]
         kernels = []
         for name, nbytes_, ms_, bound in kern:
             ach = nbytes_ / (ms_ * 1e-3) / 1e9
