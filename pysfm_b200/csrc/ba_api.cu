@@ -59,6 +59,16 @@ cudaError_t dev_alloc(T** p, size_t count) {
   return cudaMemset(*p, 0, count * sizeof(T));
 }
 
+// Wait for a stream by polling (the host-driven trial is ~0.6 ms long and its caller wants the result
+// NOW: a blocking cudaStreamSynchronize adds the wake-up latency of the driver's interrupt path, tens
+// of microseconds, to every trial).
+cudaError_t spin_sync(cudaStream_t st) {
+  cudaError_t e;
+  while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+  }
+  return e;
+}
+
 bool bound(const Context& c) {
   return c.pt_ptr && c.obs_cam && c.obs_uv && c.cam_slot && c.pt_slot && c.state.cam_R &&
          c.state.cam_t && c.state.pts;
@@ -404,7 +414,7 @@ int ba_read_scalars(ba_handle h, double* cost, double* cand_cost, int* solve_sta
   BA_ON_DEVICE(h);
   ba::Scalars s;
   BA_CUDA(h, cudaMemcpyAsync(&s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, st));
-  BA_CUDA(h, cudaStreamSynchronize(st));
+  BA_CUDA(h, spin_sync(st));
   if (cost) *cost = s.cost;
   if (cand_cost) *cand_cost = s.cand_cost;
   if (solve_status) {
@@ -462,7 +472,7 @@ int ba_trial_host_packed(ba_handle h, const double* in_host, double damping, dou
   if ((rc = ba_solve(h, cam_param_mask_host, stream)) != BA_OK) return rc;
   if ((rc = ba_backsub_retract_cost(h, stream)) != BA_OK) return rc;
   BA_CUDA(h, cudaMemcpyAsync(out_host, h->io_out, ((size_t)4 + h->ld + nx) * sizeof(double), cudaMemcpyDeviceToHost, st));
-  BA_CUDA(h, cudaStreamSynchronize(st));
+  BA_CUDA(h, spin_sync(st));
   return BA_OK;
 }
 

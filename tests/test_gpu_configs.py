@@ -263,3 +263,20 @@ def test_window_driver_uploads_the_measurements_once(cuda_device):
         ptrs.append(tuple(t.data_ptr() for t in keep))
     window_slam.run(b, int(g["win_size"]), device=cuda_device, verbose=False, on_window=hook)
     assert len(ptrs) >= 2 and len(set(ptrs)) == 1
+
+
+@pytest.mark.parametrize("nc,ranks", [(199, 2), (499, 4), (120, 8)])
+def test_distributed_solve_with_virtual_ranks_on_one_gpu(nc, ranks, cuda_device):
+    """The distributed reduced solve (ba_solve.cu, chol_dataflow_kernel<true>) needs several GPUs in
+    production; its whole protocol -- tile ownership, contribution sums, tile / inverse / y pushes,
+    flags, start barrier, replicated backward substitution -- also runs with N "virtual ranks" on ONE
+    GPU (N contexts whose peer pointers point at each other, N co-resident launches), which is what
+    tools/microbench/dist_solve_bench does: residual against the dense system <= 1e-9, status 0 and
+    identical bits of dC on every rank, or it exits non-zero."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tools", "microbench", "dist_solve_bench")
+    if not os.path.isfile(exe):
+        pytest.skip("tools/microbench/dist_solve_bench not built (__graft_entry__.build() builds it)")
+    res = subprocess.run([exe, str(nc), str(ranks), "2"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and res.stdout.rstrip().endswith("OK"), res.stdout[-2000:] + res.stderr[-2000:]
