@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
       const unsigned int* mine = reinterpret_cast<const unsigned int*>(g.base[g.rank] + dl.bar) + tid;
       unsigned int spins = 0;
       BA_PROF_T0();
-      while (ld_acquire_sys(mine) != epoch) {
+      while ((int)(ld_acquire_sys(mine) - epoch) < 0) {   // (a peer may already be one solve ahead)
         if (spin_expired(g, spins, s_t0)) break;
         __nanosleep(100);
       }

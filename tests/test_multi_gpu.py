@@ -30,6 +30,34 @@ def _free_port():
     return p
 
 
+def _guard(fn):
+    """Run a spawned worker and leave its traceback where the parent can show it."""
+    import functools
+    import traceback
+
+    @functools.wraps(fn)
+    def wrapped(rank, world, port, out_dir, *rest):
+        try:
+            return fn(rank, world, port, out_dir, *rest)
+        except BaseException:
+            with open(os.path.join(out_dir, "rank%d.err" % rank), "w") as f:
+                f.write(traceback.format_exc())
+            raise
+    return wrapped
+
+
+def _spawn(fn, world, args):
+    """mp.spawn with the workers' own tracebacks attached to a failure."""
+    import glob
+    import torch.multiprocessing as mp
+    out_dir = args[1]
+    try:
+        mp.spawn(fn, args=(world,) + tuple(args), nprocs=world, join=True)
+    except Exception as exc:
+        notes = "".join("\n--- %s ---\n%s" % (os.path.basename(p), open(p).read()) for p in sorted(glob.glob(os.path.join(out_dir, "rank*.err"))))
+        raise AssertionError("a rank failed: %s%s" % (exc, notes))
+
+
 def _init(rank, world, port, env):
     import torch
     import torch.distributed as dist
@@ -43,6 +71,7 @@ def _init(rank, world, port, env):
     return dist
 
 
+@_guard
 def _worker(rank, world, port, out_dir, collective):
     dist = _init(rank, world, port, {"PYSFM_B200_COLLECTIVE": collective, "PYSFM_B200_DIST_SOLVE_MIN_TILES": "0"})
     try:
@@ -84,7 +113,7 @@ def test_sharded_update_staged_api_and_trajectory(world, collective, tmp_path, c
     from pysfm_b200 import synthetic
     from pysfm_b200.bundle_adjuster import BundleAdjuster
     from conftest import relerr
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), collective), nprocs=world, join=True)
+    _spawn(_worker, world, (_free_port(), str(tmp_path), collective))
     got = np.load(os.path.join(str(tmp_path), "mgpu.npz"))
     a = synthetic.make_arrays(**SCENE)
     nc, nt = SCENE["n_cam"], SCENE["n_pt"]
@@ -114,6 +143,7 @@ def test_sharded_update_staged_api_and_trajectory(world, collective, tmp_path, c
     assert relerr(got["pts"], ba.bundle.reconstruction) < 1e-7
 
 
+@_guard
 def _dist_worker(rank, world, port, out_dir):
     dist = _init(rank, world, port, {"PYSFM_B200_COLLECTIVE": "peer", "PYSFM_B200_DIST_SOLVE_MIN_TILES": "1"})
     try:
@@ -158,7 +188,7 @@ def test_distributed_reduced_solve(world, tmp_path, cuda_device):
     from pysfm_b200 import synthetic
     from pysfm_b200.bundle_adjuster import BundleAdjuster
     from conftest import relerr
-    mp.spawn(_dist_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    _spawn(_dist_worker, world, (_free_port(), str(tmp_path)))
     got = np.load(os.path.join(str(tmp_path), "dist.npz"))
     a = synthetic.make_arrays(**SCENE_DIST)
     nc, nt = SCENE_DIST["n_cam"], SCENE_DIST["n_pt"]
