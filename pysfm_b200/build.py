@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libba_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
 SOURCES = ["ba_api.cu", "ba_kernels.cu", "ba_solve.cu", "ba_comm.cu", "ba_pack.cu"]
-HEADERS = ["ba_math.cuh", "ba_context.h", "ba_peer.cuh", os.path.join("..", "..", "include", "ba_b200.h")]
+HEADERS = ["ba_math.cuh", "ba_context.h", "ba_peer.cuh", "ba_solve_tc.cuh", os.path.join("..", "..", "include", "ba_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

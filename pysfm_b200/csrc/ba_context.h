@@ -146,6 +146,19 @@ struct Context {
   int strict_flags = 0;                     // BA_OPT_STRICT_FLAGS: release/acquire flag publication in the solver
   int solve_grid_cap = 0;                   // BA_OPT_SOLVE_GRID_CAP: at most this many solver CTAs (0 = one per SM)
   int split_min_tiles = 32;                 // diagonal-update tasks take over part of the chain tasks from this many tile rows on
+  // blocked solve with the tcgen05 trailing update (ba_solve_tc.cuh; single-GPU handles, large systems)
+  int tc_min_tiles = 0;                     // BA_OPT_TC_MIN_TILES: tile rows from which ba_solve takes this path (0 = never)
+  int tc_slices_n = 6;                      // BA_OPT_TC_SLICES: INT8 slices per FP64 operand (4 .. 7)
+  int tc_window = 8;                        // BA_OPT_TC_WINDOW: tile columns per panel (even, <= 16): K = 64 * window
+  int tc_bk = 64;                           // BA_OPT_TC_BK: bytes of K per pipeline stage = swizzle span (64 or 128)
+  signed char* tc_slices = nullptr;         // [slices][ld_pad][64 * window] INT8 digits of the current panel, K-major
+  double* tc_scale = nullptr;               // [ld_pad] power-of-two row scales of the current panel
+  double* tc_save = nullptr;                // [64] right-hand side block the window launch's last chain task overwrites
+  int* tc_dbg = nullptr;                    // tests: raw level sums of the next trailing update ([slices][ld_pad][tc_dbg_ld])
+  int tc_dbg_ld = 0;
+  int tc_cfg[4] = {0, 0, 0, 0};             // (slices, window, bk, ld) the buffers and tensor maps were built for
+  alignas(64) unsigned char tc_map_a[128];  // CUtensorMap: box 128 rows x bk bytes
+  alignas(64) unsigned char tc_map_b[128];  // CUtensorMap: box  64 rows x bk bytes
   unsigned int* solve_abort = nullptr;      // [1] set by a spin-wait that ran past the deadline
   unsigned long long* solve_prof = nullptr; // [16] wait-time profile of the solver (ba_solver_profile)
   bool solve_prof_on = false;               // BA_OPT_SOLVER_PROFILE
@@ -165,6 +178,7 @@ cudaError_t launch_triangulate(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
+bool tc_solve_selected(const Context& c);
 bool dist_solve_selected(const Context& c);
 
 }  // namespace ba

@@ -54,6 +54,7 @@ constexpr int NBP = NB + 1;        // padded row of the diagonal-tile work array
 constexpr int kSolveThreads = 256;
 // A quiet NaN with a payload no arithmetic produces: marks entries of x that are not computed yet.
 constexpr long long kNotYet = 0x7ff8dead0000beefLL;
+constexpr int kPhaseAll = 0, kPhaseWindow = 1, kPhaseBackward = 2;
 constexpr int kDiagTask = 0x40000000;   // task code of the distributed solve: diagonal-update task D_j (low 16 bits = j)
 
 // ------------------------------------------------------------------------------------------
@@ -270,6 +271,11 @@ struct CholArgs {
   int world, rank;
   const int* __restrict__ tasks;      // this rank's tasks in global ticket order: (i << 16) | j, chain task C_j as (j, j)
   int ntasks;
+  // ---- windowed use by the blocked tcgen05 solver (ba_solve_tc.cuh; single GPU only) ----
+  int phase;                          // kPhaseAll: factor + substitute; kPhaseWindow: the first `window_tasks` tile tickets only
+                                      // (the leading tile columns of the matrix at A), no backward substitution;
+                                      // kPhaseBackward: backward substitution only, over a factor finished by earlier launches
+  int window_tasks;
   double* base[kMaxPeers];            // DistLayout section of every rank (own rank included), peer-mapped
 };
 
@@ -499,7 +505,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   const int R0 = 32 * (wid & 1), C0 = 16 * (wid >> 1);
   const int T = g.T;
   const size_t ld = (size_t)g.ld;
-  const int ntasks = DIST ? g.ntasks : 1 + (T - 1) * (T + 2) / 2;   // C_0, then per column: diagonal-update task, chain task, the panels below
+  // C_0, then per column: diagonal-update task, chain task, the panels below
+  const int ntasks = DIST ? g.ntasks : g.phase == kPhaseWindow ? g.window_tasks : g.phase == kPhaseBackward ? 0 : 1 + (T - 1) * (T + 2) / 2;
   const unsigned int epoch = g.epoch;
   const DistLayout dl = dist_layout(g.ld);
   if (tid == 0) s_t0 = global_ns();
@@ -1487,7 +1494,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
   double* const part = buf;            // [4][NB] partial sums
   double* const accv = vec;            // [NB]
   double* const LTs = buf + 8 * NB;    // [NB][NBP] padded copy of LinvT
+  const bool factor_done = !DIST && g.phase == kPhaseBackward;   // earlier launches finished the factor: nothing to wait for but the x_i
   for (;;) {
+    if (!DIST && g.phase == kPhaseWindow) break;
     __syncthreads();
     if (tid == 0) s_task = (int)atomicAdd(&g.tickets[1], 1u);
     __syncthreads();
@@ -1500,11 +1509,13 @@ __global__ void __launch_bounds__(kSolveThreads, 1) chol_dataflow_kernel(const C
     // everything this task reads except the x_i is long finished when it starts: wait for all of
     // it at once, fetch L_kk^{-1} and y_k, and keep the NEXT tile's share in registers so that only
     // the flag hop and the 512-byte x_i sit between x_{k+1} becoming ready and x_k going out
-    wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0, kProfBackward);   // L_kk^{-1}
-    wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0, kProfBackward);                        // y_k
+    if (!factor_done) {
+      wait_flag<DIST>(g, &g.flags[solve_rowflag_base(T) + (size_t)k * 8 + 7], epoch, s_t0, kProfBackward);   // L_kk^{-1}
+      wait_flag<DIST>(g, &g.flags[(size_t)T * T + T + k], epoch, s_t0, kProfBackward);                        // y_k
+    }
     // tiles (i, k), i > k: one flag per thread, polled side by side (a single thread walking down a
     // column of 188 flags is 188 dependent L2 round trips in front of every task)
-    for (int i0 = T - 1; i0 > k; i0 -= kSolveThreads) {
+    for (int i0 = T - 1; i0 > k && !factor_done; i0 -= kSolveThreads) {
       const int i = i0 - tid;
       if (i > k) {
         const unsigned int* f = &g.flags[(size_t)i * T + k];
@@ -1684,8 +1695,138 @@ static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st
   return cudaGetLastError();
 }
 
+}  // namespace ba
+#include "ba_solve_tc.cuh"
+namespace ba {
+
+// ------------------------------------------------------------------------------------------
+// Blocked solve, trailing updates on tcgen05 (ba_solve_tc.cuh has the algorithm).
+bool tc_solve_selected(const Context& c) {
+  return c.tc_min_tiles > 0 && c.ld / NB >= c.tc_min_tiles && c.ld / NB > c.tc_window + 1 && !dist_solve_selected(c);
+}
+
+static cudaError_t tc_prepare(Context& c) {
+  const int ld = c.ld, w = c.tc_window, K = NB * w, S = c.tc_slices_n;
+  if (c.tc_slices && c.tc_cfg[0] == S && c.tc_cfg[1] == w && c.tc_cfg[2] == c.tc_bk && c.tc_cfg[3] == ld) return cudaSuccess;
+  if (S < 4 || S > 7 || w < 2 || w > tc::kMaxWindowTiles || (w & 1) || (c.tc_bk != 64 && c.tc_bk != 128)) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (c.tc_slices) { cudaFree(c.tc_slices); c.tc_slices = nullptr; }
+  if (c.tc_scale) { cudaFree(c.tc_scale); c.tc_scale = nullptr; }
+  const size_t ld_pad = ((size_t)ld + 127) / 128 * 128;
+  const size_t bytes = (size_t)S * ld_pad * K;
+  if ((e = cudaMalloc((void**)&c.tc_slices, bytes)) != cudaSuccess) return e;
+  if ((e = cudaMemset(c.tc_slices, 0, bytes)) != cudaSuccess) return e;   // rows ld .. ld_pad stay zero for good
+  if ((e = cudaMalloc((void**)&c.tc_scale, ld_pad * sizeof(double))) != cudaSuccess) return e;
+  if ((e = cudaMemset(c.tc_scale, 0, ld_pad * sizeof(double))) != cudaSuccess) return e;
+  if (!c.tc_save && (e = cudaMalloc((void**)&c.tc_save, 64 * sizeof(double))) != cudaSuccess) return e;
+  static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap");
+  if (!tc::make_slice_map(reinterpret_cast<CUtensorMap*>(c.tc_map_a), c.tc_slices, K, (size_t)S * ld_pad, c.tc_bk, tc::kM) ||
+      !tc::make_slice_map(reinterpret_cast<CUtensorMap*>(c.tc_map_b), c.tc_slices, K, (size_t)S * ld_pad, c.tc_bk, tc::kN)) {
+    c.last_error = "cuTensorMapEncodeTiled failed (driver entry point missing or arguments rejected)";
+    return cudaErrorUnknown;
+  }
+  c.tc_cfg[0] = S; c.tc_cfg[1] = w; c.tc_cfg[2] = c.tc_bk; c.tc_cfg[3] = ld;
+  return cudaSuccess;
+}
+
+// The trailing update of one panel: A[c1.., c1..] -= L[c1.., c0..c1) L[c1.., c0..c1)^T (lower triangle), plus
+// the slices, the scales and the right-hand side update that go with it.  `saved_rhs`: see window_prep_kernel.
+cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0, const double* saved_rhs, cudaStream_t st) {
+  const int ld = c.ld, K = NB * c.tc_window, c1 = c0 + K;
+  const int ld_pad = (ld + 127) / 128 * 128;
+  cudaError_t e;
+  if ((e = tc::launch_slice(c.tc_slices_n, A, ld, c0, K, rhs, saved_rhs, reinterpret_cast<int8_t*>(c.tc_slices), (size_t)ld_pad * K,
+                            c.tc_scale, st)) != cudaSuccess) return e;
+  c.launches += 1;
+  tc::SyrkArgs g;
+  memset(&g, 0, sizeof g);
+  g.A = A; g.scale = c.tc_scale; g.status = &c.scalars->status; g.abort = c.solve_abort;
+  g.ld = ld; g.ld_pad = ld_pad; g.c1 = c1; g.K = K;
+  g.n_nb = (ld - c1) / tc::kN;
+  g.ntiles = tc::count_tiles(g.n_nb);
+  g.dbg_acc = c.tc_dbg; g.dbg_ld = c.tc_dbg ? c.tc_dbg_ld : 0;
+  if (g.ntiles <= 0) return cudaSuccess;
+  int grid = g.ntiles < c.num_sms ? g.ntiles : c.num_sms;
+  if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
+  e = tc::launch_syrk(c.tc_slices_n, c.tc_bk, *reinterpret_cast<const CUtensorMap*>(c.tc_map_a),
+                      *reinterpret_cast<const CUtensorMap*>(c.tc_map_b), g, grid, st);
+  c.launches += 1;
+  return e;
+}
+
+static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) {
+  const int ld = c.ld, T = ld / NB, w = c.tc_window;
+  cudaError_t e;
+  if ((e = tc_prepare(c)) != cudaSuccess) return e;
+  const double* packed = (c.sys_state == kSysReduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
+  double* const A = c.Adense;
+  double* const rhs = c.Adense + (size_t)ld * ld;
+  expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask, A, rhs, c.solve_tickets,
+                                           &c.scalars->status, c.dC, c.solve_abort, nullptr, 1.0);
+  c.launches += 1;
+  if (!c.solve_attr_set) {
+    if ((e = cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSolveSmemBytes)) != cudaSuccess) return e;
+    c.solve_attr_set = true;
+  }
+  CholArgs g;
+  memset(&g, 0, sizeof g);
+  g.flags = c.solve_flags;
+  g.tickets = c.solve_tickets;
+  g.status = &c.scalars->status;
+  g.ld = ld;
+  g.abort = c.solve_abort;
+  g.spin_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
+  g.strict = c.strict_flags;
+  g.world = 1; g.rank = 0;
+  g.x = c.dC;
+  for (int j0 = 0; j0 < T; j0 += w) {
+    const int Tw = T - j0;                       // tile rows of the trailing matrix
+    const bool last = Tw <= w + 1;               // what is left is one window: factor it all
+    const int c0 = j0 * NB;
+    // tickets of the leading w tile columns: C_0, then per column jc < w the T' - jc tasks D_{jc+1}, C_{jc+1}, (jc+2.., jc)
+    const int ntasks = last ? 1 + (Tw - 1) * (Tw + 2) / 2 : 1 + w * Tw - w * (w - 1) / 2;
+    double* const rhs_below = last ? nullptr : rhs + c0 + w * NB;
+    tc::window_prep_kernel<<<1, 64, 0, st>>>(c.solve_tickets, rhs_below, c.tc_save);
+    c.launches += 1;
+    g.A = A + (size_t)c0 * ld + c0;
+    g.rhs = rhs + c0;
+    g.LinvT = c.LinvT + (size_t)j0 * NB * NB;
+    g.Wpart = c.Wpart + (size_t)j0 * (NB * NB + NB);
+    g.T = Tw;
+    g.epoch = ++c.solve_epoch;
+    g.phase = kPhaseWindow;
+    g.window_tasks = ntasks;
+    g.split = 0;
+    g.prof = nullptr;
+    int grid = ntasks < c.num_sms ? ntasks : c.num_sms;
+    if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
+    chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
+    c.launches += 1;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (last) break;
+    if ((e = launch_tc_trailing_update(c, A, rhs, c0, c.tc_save, st)) != cudaSuccess) return e;
+  }
+  // backward substitution over the finished factor
+  g.A = A;
+  g.rhs = rhs;
+  g.LinvT = c.LinvT;
+  g.Wpart = c.Wpart;
+  g.T = T;
+  g.epoch = ++c.solve_epoch;
+  g.phase = kPhaseBackward;
+  g.window_tasks = 0;
+  tc::window_prep_kernel<<<1, 64, 0, st>>>(c.solve_tickets, nullptr, c.tc_save);
+  int grid = T < c.num_sms ? T : c.num_sms;
+  if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
+  chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
+  c.launches += 2;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st) {
   if (dist_solve_selected(c)) return launch_solve_dist(c, have_mask, st);
+  if (tc_solve_selected(c)) return launch_solve_tc(c, have_mask, st);
   const int ld = c.ld, T = ld / NB;
   cudaError_t e;
   // sharded problems: factor the all-reduced copy the peers pushed (ba_comm.cu), not the local contribution

@@ -1,0 +1,488 @@
+// Large reduced camera systems on the 5th-generation tensor cores:  solve_motion_normal_eqns
+// (bundle_adjuster.py:281-312) as a BLOCKED right-looking Cholesky whose trailing update
+//     A22 -= L21 L21^T          (87 % of the flops at 2,000 cameras)
+// runs as exact INT8 products on tcgen05 (SASS UTCIMMA) with INT32 accumulators in tensor memory,
+// fed by TMA tensor-map loads (UTMALDG), instead of FP64 DMMA.  tcgen05 has no FP64 kind, so the
+// FP64 operand is split Ozaki-style:
+//
+//   row i of the panel L21 (K = 64 w columns) is scaled by a power of two, x = L_ik 2^-e_i in (-1, 1),
+//   and cut into S signed 7-bit digits:  x = sum_p d_p 2^(-6-7p) + O(2^-7S),  d_p in [-64, 64]  (exact in
+//   FP64: slice_panel_kernel).  Then
+//        sum_k L_ik L_jk = 2^(e_i+e_j) sum_{p,q} 2^(-12-7(p+q)) sum_k d_p[i,k] d_q[j,k]
+//   and every inner sum is an INT8 x INT8 -> INT32 product that the tensor core evaluates EXACTLY
+//   (|sum| <= 64*64*K*(level+1) < 2^31).  Pairs of one level l = p+q share a weight and accumulate
+//   into ONE TMEM accumulator (S accumulators of 128 x 64 INT32 = 64 S <= 448 of the 512 TMEM
+//   columns); levels l >= S are dropped (relative 2^-7S of the row scales: 2^-42 at S = 6).  The
+//   epilogue reads the S accumulators back (tcgen05.ld), combines them in FP64 by Horner from the
+//   smallest level up (exact scalings, one rounding per level) and subtracts from A in place.
+//
+// What stays on the FP64 pipe: the panel (diagonal block + the tiles below it, 13 % of the flops
+// at w = 8), factored by the SAME dataflow kernel as the small systems, launched on the leading w
+// tile columns of the trailing matrix (CholArgs::phase = kPhaseWindow), the forward substitution
+// inside it, and the backward substitution (one launch, kPhaseBackward).  Per window:
+//
+//   window_prep_kernel      ticket reset; saves the right-hand side of the tile row right below the
+//                           window (the window launch's last chain task C_w overwrites it with a y_w
+//                           that lacks this window's terms)
+//   chol_dataflow_kernel    L11, L21 (all rows), L11^-1 tiles, y of the window        [DMMA]
+//   slice_panel_kernel      row scales + S INT8 slice matrices of L21 (K-major, the TMA source) and
+//                           b[rows below] -= L21 y_window                              [FP64, HBM-bound]
+//   ozaki_syrk_kernel       A22 -= L21 L21^T, lower triangle, 128 x 64 tiles, persistent,
+//                           warp-specialised: TMA producer / MMA issuer / 4 epilogue warps  [tcgen05]
+//
+// Accuracy (oracle/ozaki_model.py restates the arithmetic in numpy; tests/test_ozaki_model.py):
+// S = 6 reproduces the FP64 solve of BA reduced systems to ~1e-11 relative at condition 1e4
+// (S = 5: 1e-9, S = 7: FP64 level); the int8 slices and INT32 level sums are bit-exact by
+// construction and are tested as such against the numpy model on the GPU.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace ba {
+namespace tc {
+
+constexpr int kM = 128;          // rows of an output tile (UMMA M, one TMEM lane per row)
+constexpr int kN = 64;           // columns of an output tile (UMMA N)
+constexpr int kThreads = 192;    // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, warps 2-5: epilogue
+constexpr int kMaxStages = 8;
+constexpr int kMaxWindowTiles = 16;
+constexpr unsigned long long kWaitLimitNs = 3000000000ull;   // a barrier that has not moved for 3 s is a bug: give up, report
+
+struct SyrkArgs {
+  double* __restrict__ A;             // dense lower, column-major, ld
+  const double* __restrict__ scale;   // [ld_pad] 2^(e_i - 6)
+  double* __restrict__ status;        // solver status word (2 = a wait ran past its deadline)
+  unsigned int* __restrict__ abort;   // != 0: an earlier launch of this solve gave up
+  int* __restrict__ dbg_acc;          // optional [S][ld_pad... ] dump of the raw level sums (tests): see dbg_ld
+  int ld, ld_pad;
+  int c1;        // first row / column of the trailing matrix (multiple of 128)
+  int K;         // panel width = contraction length (multiple of BK)
+  int n_nb;      // 64-wide column blocks of the trailing matrix
+  int ntiles;
+  int stages;
+  int dbg_ld;    // row pitch of dbg_acc (0 = off)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: false = the launch is being abandoned (this wait or another one ran out of time).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* s_abort, unsigned long long t0) {
+  unsigned int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0u) {
+      if (*s_abort) return false;
+      if (now_ns() - t0 > kWaitLimitNs) {
+        *s_abort = 1;
+        return false;
+      }
+    }
+  }
+  return *s_abort == 0;
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {   // arrives on `bar` when every MMA issued so far by this thread is done
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]^T, INT8 x INT8 -> INT32, issued by ONE thread for the CTA
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile whose rows are BK bytes wide and
+// swizzled over BK bytes (cute::UMMA::SmemDescriptor): start address >> 4 | LBO (unused for
+// swizzled K-major, 1) << 16 | SBO (8 rows) >> 4 << 32 | version 1 << 46 | layout type << 61.
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = BK == 128 ? 2ull : BK == 64 ? 4ull : 6ull;   // SWIZZLE_128B / 64B / 32B
+  constexpr uint64_t sbo = (8ull * BK) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3fffu) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::i8: D = S32 (2 << 4), A and B signed
+// 8-bit (1 << 7, 1 << 10), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+// tile t of the trailing matrix's lower triangle -> (128-row block, 64-column block), both relative
+// to c1: row block m holds column blocks 0 .. 2m+1 (the last row block of an odd n_nb one less)
+__host__ __device__ __forceinline__ void decode_tile(int t, int& mbl, int& nbl) {
+  int m = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (m > 0 && m * (m + 1) > t) --m;
+  while ((m + 1) * (m + 2) <= t) ++m;
+  mbl = m;
+  nbl = t - m * (m + 1);
+}
+__host__ __device__ __forceinline__ int count_tiles(int n_nb) {
+  const int mb = (n_nb + 1) / 2;
+  return mb * (mb + 1) - (n_nb & 1);
+}
+
+template <int S, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SyrkArgs g) {
+  constexpr int A_TILE = kM * BK, B_TILE = kN * BK, STAGE = S * (A_TILE + B_TILE);
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int s_abort;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // operand tiles want 1024-byte alignment (the swizzle pattern is a function of the address bits)
+  uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const unsigned long long t0 = now_ns();
+  const int nk = g.K / BK;
+
+  if (threadIdx.x == 0) {
+    s_abort = (*g.abort != 0u) ? 1 : 0;
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: one warp allocates (and frees), the base address travels through shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  volatile int* const abortp = &s_abort;
+
+  if (warp == 0) {
+    // ================================ TMA producer ========================================
+    if (lane == 0 && *abortp == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+        int mbl, nbl;
+        decode_tile(t, mbl, nbl);
+        const int rowA = g.c1 + mbl * kM, rowB = g.c1 + nbl * kN;
+        bool ok = true;
+        for (int kc = 0; kc < nk && ok; ++kc) {
+          ok = mbar_wait(&empty_bar[stage], phase ^ 1u, abortp, t0);
+          if (!ok) break;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)STAGE);
+          uint8_t* const sA = smem + (size_t)stage * STAGE;
+          uint8_t* const sB = sA + S * A_TILE;
+#pragma unroll
+          for (int p = 0; p < S; ++p) tma_load_2d(&mapA, &full_bar[stage], sA + p * A_TILE, kc * BK, p * g.ld_pad + rowA);
+#pragma unroll
+          for (int p = 0; p < S; ++p) tma_load_2d(&mapB, &full_bar[stage], sB + p * B_TILE, kc * BK, p * g.ld_pad + rowB);
+          if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0 && *abortp == 0) {
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+        // the epilogue has drained the accumulators of the previous tile
+        if (!mbar_wait(&tmem_empty_bar, tphase ^ 1u, abortp, t0)) break;
+        tcgen05_fence_after();
+        bool ok = true;
+        for (int kc = 0; kc < nk; ++kc) {
+          ok = mbar_wait(&full_bar[stage], phase, abortp, t0);
+          if (!ok) break;
+          tcgen05_fence_after();
+          const uint32_t aA = smem_u32(smem + (size_t)stage * STAGE);
+          const uint32_t aB = aA + S * A_TILE;
+#pragma unroll
+          for (int ks = 0; ks < BK / 32; ++ks) {
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+              const uint64_t da = umma_desc<BK>(aA + p * A_TILE + ks * 32);
+#pragma unroll
+              for (int q = 0; q < S - p; ++q) {
+                const uint64_t db = umma_desc<BK>(aB + q * B_TILE + ks * 32);
+                // level p+q; its first product of the tile (p = 0, first 32 bytes of K) overwrites
+                mma_i8(tmem_base + (uint32_t)((p + q) * kN), da, db, kInstrDesc, (kc > 0 || ks > 0 || p > 0) ? 1u : 0u);
+              }
+            }
+          }
+          tcgen05_commit(&empty_bar[stage]);   // the stage is free when these products have read it
+          if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (!ok) break;
+        tcgen05_commit(&tmem_full_bar);        // all level sums of the tile are in TMEM
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    // ================================ epilogue (4 warps, thread = row) =====================
+    const int quad = warp & 3;                 // a warp reaches TMEM lanes 32 (warp % 4) .. +31 only
+    const int r = 32 * quad + lane;
+    uint32_t fphase = 0;
+    for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+      int mbl, nbl;
+      decode_tile(t, mbl, nbl);
+      const int row = g.c1 + mbl * kM + r, col0 = g.c1 + nbl * kN;
+      const bool row_ok = row < g.ld;
+      double* const Arow = g.A + (size_t)col0 * g.ld + row;
+      const double srow = row_ok ? __ldg(g.scale + row) : 0.0;
+      // pull the tile of A towards L2 while the products run (two 128-byte lines per warp and column)
+      if (row_ok && (lane & 15) == 0) {
+#pragma unroll 8
+        for (int c = 0; c < kN; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(Arow + (size_t)c * g.ld));
+      }
+      const bool ok = __all_sync(0xffffffffu, mbar_wait(&tmem_full_bar, fphase, abortp, t0));   // (tcgen05.ld is warp-collective)
+      tcgen05_fence_after();
+      if (ok) {
+#pragma unroll 1
+        for (int c8 = 0; c8 < kN / 8; ++c8) {
+          double a[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = (row_ok && row >= col0 + c8 * 8 + c) ? __ldcg(Arow + (size_t)(c8 * 8 + c) * g.ld) : 0.0;
+          int acc[S][8];
+#pragma unroll
+          for (int l = 0; l < S; ++l) tmem_ld8(tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)(l * kN + c8 * 8), acc[l]);
+          tmem_ld_wait();
+          if (g.dbg_ld > 0 && row_ok) {
+#pragma unroll
+            for (int l = 0; l < S; ++l)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) g.dbg_acc[((size_t)l * g.ld_pad + row) * g.dbg_ld + (col0 + c8 * 8 + c)] = acc[l][c];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = S - 1; l >= 0; --l) v = v * 0.0078125 + (double)acc[l][c];   // Horner in 2^-7, smallest level first
+            const int col = col0 + c8 * 8 + c;
+            if (row_ok && row >= col) Arow[(size_t)(c8 * 8 + c) * g.ld] = a[c] - (v * srow) * __ldg(g.scale + col);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar);
+      fphase ^= 1u;
+      if (!ok) break;
+    }
+  }
+
+  // ---- teardown: everybody is done with TMEM before its owner frees it ----
+  tcgen05_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && s_abort && *g.abort == 0u) {
+    atomicExch(g.abort, 1u);
+    *g.status = 2.0;
+  }
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row scales, S INT8 slice matrices (K-major: slices[p][row][k], row pitch K bytes) of the panel
+// L[c1.., c0..c1) and the right-looking update of the right-hand side, b[row] -= sum_k L[row,k] y[k].
+// One CTA per 64 rows; thread = (row r, quarter g of the columns).
+template <int S>
+__global__ void __launch_bounds__(256)
+slice_panel_kernel(const double* __restrict__ A, int ld, int c0, int K, double* __restrict__ rhs,
+                   const double* __restrict__ saved_rhs, int8_t* __restrict__ slices, size_t slice_stride,
+                   double* __restrict__ scale) {
+  __shared__ double s_y[64 * kMaxWindowTiles];
+  __shared__ double s_mx[4][64], s_dot[4][64], s_mul[64];
+  const int tid = threadIdx.x, r = tid & 63, gq = tid >> 6;
+  const int c1 = c0 + K, R0 = c1 + 64 * blockIdx.x;
+  for (int k = tid; k < K; k += 256) s_y[k] = rhs[c0 + k];   // y of the window (written by its chain tasks)
+  __syncthreads();
+  const double* const col = A + (size_t)c0 * ld + R0 + r;
+  {
+    double mx = 0.0, dot = 0.0;
+#pragma unroll 8
+    for (int k = gq; k < K; k += 4) {
+      const double v = __ldcg(col + (size_t)k * ld);
+      mx = fmax(mx, fabs(v));
+      dot = fma(v, s_y[k], dot);
+    }
+    s_mx[gq][r] = mx;
+    s_dot[gq][r] = dot;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const double mx = fmax(fmax(s_mx[0][r], s_mx[1][r]), fmax(s_mx[2][r], s_mx[3][r]));
+    const double dot = (s_dot[0][r] + s_dot[1][r]) + (s_dot[2][r] + s_dot[3][r]);
+    // |x| 2^-e < 1  (mx = f 2^e, f in [0.5, 1));  non-finite rows (a failed pivot upstream) get e = 0
+    const int e = (mx > 0.0 && mx < 1.7e308) ? ilogb(mx) + 1 : 0;
+    s_mul[r] = scalbn(1.0, 6 - e);
+    scale[R0 + r] = scalbn(1.0, e - 6);
+    // the tile row right below the window: its b was saved before the window launch overwrote it
+    const double b = (blockIdx.x == 0 && saved_rhs) ? saved_rhs[r] : rhs[R0 + r];
+    rhs[R0 + r] = b - dot;
+  }
+  __syncthreads();
+  const double mul = s_mul[r];
+  for (int kc = 0; kc < K; kc += 64) {
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __ldcg(col + (size_t)(kc + 16 * gq + i) * ld) * mul;
+    uint32_t pk[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p) pk[p][0] = pk[p][1] = pk[p][2] = pk[p][3] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double t = v[i];
+      if (!(fabs(t) <= 64.0)) t = 0.0;   // NaN / Inf
+#pragma unroll
+      for (int p = 0; p < S; ++p) {
+        const double d = rint(t);
+        pk[p][i >> 2] |= ((uint32_t)(int)d & 0xffu) << (8 * (i & 3));
+        t = (t - d) * 128.0;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+      *reinterpret_cast<uint4*>(slices + (size_t)p * slice_stride + (size_t)(R0 + r) * K + kc + 16 * gq) =
+          make_uint4(pk[p][0], pk[p][1], pk[p][2], pk[p][3]);
+  }
+}
+
+// ticket reset of the next window launch + copy of the right-hand side block its last chain task clobbers
+__global__ void window_prep_kernel(unsigned int* __restrict__ tickets, const double* __restrict__ rhs_block, double* __restrict__ save) {
+  if (threadIdx.x == 0) {
+    tickets[0] = 0u;
+    tickets[1] = 0u;
+  }
+  if (rhs_block && threadIdx.x < 64) save[threadIdx.x] = rhs_block[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// tensor map over the slice matrices seen as ONE 2-D UINT8 tensor [S * ld_pad rows][K bytes], box = box_rows x bk bytes
+inline bool make_slice_map(CUtensorMap* map, const void* base, int K, size_t rows, int bk, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K};
+  const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapSwizzle sw = bk == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int S, int BK>
+inline size_t syrk_stage_bytes() { return (size_t)S * (kM + kN) * BK; }
+
+// stages that fit the opt-in shared memory (227 KB minus the static part and the alignment slack)
+template <int S, int BK>
+inline int syrk_stages() {
+  const size_t budget = 232448 - 2048;
+  int st = (int)(budget / syrk_stage_bytes<S, BK>());
+  if (st > kMaxStages) st = kMaxStages;
+  return st;
+}
+
+template <int S, int BK>
+inline cudaError_t launch_syrk_t(const CUtensorMap& mapA, const CUtensorMap& mapB, SyrkArgs g, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  g.stages = syrk_stages<S, BK>();
+  if (g.stages < 1) return cudaErrorInvalidConfiguration;
+  const size_t smem = (size_t)g.stages * syrk_stage_bytes<S, BK>() + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_syrk_kernel<S, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  ozaki_syrk_kernel<S, BK><<<grid, kThreads, smem, st>>>(mapA, mapB, g);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_syrk(int S, int bk, const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st) {
+  if (bk == 128) {
+    switch (S) {
+      case 4: return launch_syrk_t<4, 128>(mapA, mapB, g, grid, st);
+      case 5: return launch_syrk_t<5, 128>(mapA, mapB, g, grid, st);
+      case 6: return launch_syrk_t<6, 128>(mapA, mapB, g, grid, st);
+      case 7: return launch_syrk_t<7, 128>(mapA, mapB, g, grid, st);
+    }
+  } else if (bk == 64) {
+    switch (S) {
+      case 4: return launch_syrk_t<4, 64>(mapA, mapB, g, grid, st);
+      case 5: return launch_syrk_t<5, 64>(mapA, mapB, g, grid, st);
+      case 6: return launch_syrk_t<6, 64>(mapA, mapB, g, grid, st);
+      case 7: return launch_syrk_t<7, 64>(mapA, mapB, g, grid, st);
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_slice(int S, const double* A, int ld, int c0, int K, double* rhs, const double* saved_rhs, int8_t* slices,
+                                size_t slice_stride, double* scale, cudaStream_t st) {
+  const int blocks = (ld - (c0 + K)) / 64;
+  if (blocks <= 0) return cudaSuccess;
+  switch (S) {
+    case 4: slice_panel_kernel<4><<<blocks, 256, 0, st>>>(A, ld, c0, K, rhs, saved_rhs, slices, slice_stride, scale); break;
+    case 5: slice_panel_kernel<5><<<blocks, 256, 0, st>>>(A, ld, c0, K, rhs, saved_rhs, slices, slice_stride, scale); break;
+    case 6: slice_panel_kernel<6><<<blocks, 256, 0, st>>>(A, ld, c0, K, rhs, saved_rhs, slices, slice_stride, scale); break;
+    case 7: slice_panel_kernel<7><<<blocks, 256, 0, st>>>(A, ld, c0, K, rhs, saved_rhs, slices, slice_stride, scale); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace ba

@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 names="$*"
-[ -n "$names" ] || names="solve_bench dist_solve_bench red_bench bulk_issue_bench dmma_bench lat_bench tile_bench"
+[ -n "$names" ] || names="solve_bench tc_bench dist_solve_bench red_bench bulk_issue_bench dmma_bench lat_bench tile_bench"
 for n in $names; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --fmad=true -o "$n" "$n.cu"
   echo "built $n"
