@@ -74,9 +74,18 @@ enum {
   BA_OPT_DIST_BAND = 3,            /* distributed solve: tiles with i - j <= band stay on rank 0 */
   BA_OPT_SOLVE_GRID_CAP = 4,       /* at most this many solver CTAs (0 = one per SM) */
   BA_OPT_SOLVER_PROFILE = 5,       /* 1: the solver accumulates its wait-time profile (ba_solver_profile) */
-  BA_OPT_FUSE_COST_REDUCTION = 6   /* sharded handles over peer memory (default 1): ba_backsub_retract_cost reduces
+  BA_OPT_FUSE_COST_REDUCTION = 6,  /* sharded handles over peer memory (default 1): ba_backsub_retract_cost reduces
                                       {cost, candidate cost} over the ranks in its own epilogue and the following
                                       ba_allreduce_costs is a no-op; set the same value on every rank */
+  BA_OPT_TC_MIN_TILES = 7,         /* ba_solve takes the blocked factorisation whose trailing updates run as INT8
+                                      products on tcgen05 (Ozaki slices of the FP64 panel, exact INT32 sums in
+                                      tensor memory, FP64 recombination) when the reduced system has at least this
+                                      many 64-wide tile rows and is not solved distributed (default 96, i.e. >= 1024
+                                      cameras; 0 = never: FP64 DMMA only) */
+  BA_OPT_TC_SLICES = 8,            /* INT8 slices per FP64 operand, 4 .. 7 (default 6: trailing updates to 2^-42 of
+                                      the row scales; 7 = FP64 level; each step fewer is ~25 % faster and 128x coarser) */
+  BA_OPT_TC_WINDOW = 9,            /* tile columns per panel of the blocked factorisation (even, 2 .. 16; default 8) */
+  BA_OPT_TC_BK = 10                /* bytes of the contraction per pipeline stage = TMA/UMMA swizzle span (64 or 128) */
 };
 
 enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */

@@ -171,7 +171,8 @@ int ba_destroy(ba_handle h) {
   DeviceGuard guard__(h->device);
   void* ptrs[] = {h->Vinv, h->bP, h->V, h->U, h->bC, h->W, h->io_out, h->obs_r, h->obs_Jc,
                   h->obs_Jp, h->delta_cam, h->delta_pt, h->cam_mask, h->partials, h->counters,
-                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->solve_prof, h->dist_tasks, h->diag_rep};
+                  h->Adense, h->LinvT, h->Wpart, h->solve_flags, h->solve_tickets, h->solve_abort, h->solve_prof, h->dist_tasks, h->diag_rep,
+                  h->tc_slices, h->tc_scale, h->tc_save};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int p = 0; p < ba::kMaxPeers; ++p)
@@ -342,6 +343,15 @@ int ba_set_option(ba_handle h, int option, double value) {
     case BA_OPT_SOLVE_GRID_CAP: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->solve_grid_cap = (int)value; break;
     case BA_OPT_SOLVER_PROFILE: h->solve_prof_on = value != 0.0; break;
     case BA_OPT_FUSE_COST_REDUCTION: h->fuse_cost_reduction = value != 0.0; break;
+    case BA_OPT_TC_MIN_TILES: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->tc_min_tiles = (int)value; break;
+    case BA_OPT_TC_SLICES: if (value < 4.0 || value > 7.0) return BA_ERR_BAD_ARGUMENT; h->tc_slices_n = (int)value; break;
+    case BA_OPT_TC_WINDOW: {
+      const int w = (int)value;
+      if (w < 2 || w > 16 || (w & 1)) return BA_ERR_BAD_ARGUMENT;
+      h->tc_window = w;
+      break;
+    }
+    case BA_OPT_TC_BK: if (value != 64.0 && value != 128.0) return BA_ERR_BAD_ARGUMENT; h->tc_bk = (int)value; break;
     default: return BA_ERR_BAD_ARGUMENT;
   }
   return BA_OK;

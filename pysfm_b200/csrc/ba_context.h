@@ -156,6 +156,8 @@ struct Context {
   double* tc_save = nullptr;                // [64] right-hand side block the window launch's last chain task overwrites
   int* tc_dbg = nullptr;                    // tests: raw level sums of the next trailing update ([slices][ld_pad][tc_dbg_ld])
   int tc_dbg_ld = 0;
+  unsigned long long* tc_dbg_time = nullptr;  // microbenchmarks: role timers of the trailing-update kernel (SyrkArgs::dbg_time)
+  int tc_dbg_skip = 0;                      // microbenchmarks: roles of the trailing-update kernel switched off (SyrkArgs::dbg_skip)
   int tc_cfg[4] = {0, 0, 0, 0};             // (slices, window, bk, ld) the buffers and tensor maps were built for
   alignas(64) unsigned char tc_map_a[128];  // CUtensorMap: box 128 rows x bk bytes
   alignas(64) unsigned char tc_map_b[128];  // CUtensorMap: box  64 rows x bk bytes

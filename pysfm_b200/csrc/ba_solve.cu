@@ -1745,6 +1745,8 @@ cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0
   g.n_nb = (ld - c1) / tc::kN;
   g.ntiles = tc::count_tiles(g.n_nb);
   g.dbg_acc = c.tc_dbg; g.dbg_ld = c.tc_dbg ? c.tc_dbg_ld : 0;
+  g.dbg_skip = c.tc_dbg_skip;
+  g.dbg_time = c.tc_dbg_time;
   if (g.ntiles <= 0) return cudaSuccess;
   int grid = g.ntiles < c.num_sms ? g.ntiles : c.num_sms;
   if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;

@@ -43,7 +43,8 @@ namespace tc {
 
 constexpr int kM = 128;          // rows of an output tile (UMMA M, one TMEM lane per row)
 constexpr int kN = 64;           // columns of an output tile (UMMA N)
-constexpr int kThreads = 192;    // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, warps 2-5: epilogue
+constexpr int kThreads = 320;    // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, warps 2-9: epilogue
+constexpr int kEpilogueThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kMaxWindowTiles = 16;
 constexpr unsigned long long kWaitLimitNs = 3000000000ull;   // a barrier that has not moved for 3 s is a bug: give up, report
@@ -53,6 +54,7 @@ struct SyrkArgs {
   const double* __restrict__ scale;   // [ld_pad] 2^(e_i - 6)
   double* __restrict__ status;        // solver status word (2 = a wait ran past its deadline)
   unsigned int* __restrict__ abort;   // != 0: an earlier launch of this solve gave up
+  unsigned long long* __restrict__ dbg_time;   // optional [8] role timers, summed over CTAs (clocks): see tc_bench perf
   int* __restrict__ dbg_acc;          // optional [S][ld_pad... ] dump of the raw level sums (tests): see dbg_ld
   int ld, ld_pad;
   int c1;        // first row / column of the trailing matrix (multiple of 128)
@@ -61,6 +63,8 @@ struct SyrkArgs {
   int ntiles;
   int stages;
   int dbg_ld;    // row pitch of dbg_acc (0 = off)
+  int dbg_skip;  // microbenchmarks only: 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work, 8 = drain without the FP64
+                 // combination, 16 = no load / store of A (results are garbage)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +133,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
+// exact INT32 -> FP64: the integer lands in the low mantissa bits of 2^52 + 2^31, one subtraction
+__device__ __forceinline__ double int_to_double(int x) {
+  return __hiloint2double(0x43300000, (int)((unsigned int)x ^ 0x80000000u)) - 4503601774854144.0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major operand tile whose rows are BK bytes wide and
@@ -142,7 +150,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::i8: D = S32 (2 << 4), A and B signed
 // 8-bit (1 << 7, 1 << 10), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
-constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+constexpr int kMaxPairs = 4;     // pairs (p, q0 .. q0+3) issued as one product with N = 256
 
 // tile t of the trailing matrix's lower triangle -> (128-row block, 64-column block), both relative
 // to c1: row block m holds column blocks 0 .. 2m+1 (the last row block of an odd n_nb one less)
@@ -158,8 +169,13 @@ __host__ __device__ __forceinline__ int count_tiles(int n_nb) {
   return mb * (mb + 1) - (n_nb & 1);
 }
 
-template <int S, int BK>
-__global__ void __launch_bounds__(kThreads, 1)
+#define TC_T0() const long long tc_t0__ = DBG && g.dbg_time ? clock64() : 0
+#define TC_ADD(slot) do { if (DBG && g.dbg_time) tc_acc[(slot)] += clock64() - tc_t0__; } while (0)
+
+// DBG = true: the instantiation behind the tests and microbenchmarks (level-sum dump, role timers,
+// roles switched off); the product launches DBG = false, where all of that is compiled out.
+template <int S, int BK, bool DBG>
+__global__ void __launch_bounds__(kThreads, 1)   // 10 warps = 3 on one scheduler's 16K registers: 168 per thread
 ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const SyrkArgs g) {
   constexpr int A_TILE = kM * BK, B_TILE = kN * BK, STAGE = S * (A_TILE + B_TILE);
   constexpr uint32_t kTmemCols = 512;
@@ -172,6 +188,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint8_t* const smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const unsigned long long t0 = now_ns();
   const int nk = g.K / BK;
+  const int skip = DBG ? g.dbg_skip : 0;
 
   if (threadIdx.x == 0) {
     s_abort = (*g.abort != 0u) ? 1 : 0;
@@ -180,7 +197,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, 128);
+    mbar_init(&tmem_empty_bar, kEpilogueThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: one warp allocates (and frees), the base address travels through shared memory
@@ -192,6 +209,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = s_tmem_base;
   volatile int* const abortp = &s_abort;
+  long long tc_acc[3] = {0, 0, 0};   // role-local timers (DBG)
 
   if (warp == 0) {
     // ================================ TMA producer ========================================
@@ -204,19 +222,28 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int rowA = g.c1 + mbl * kM, rowB = g.c1 + nbl * kN;
         bool ok = true;
         for (int kc = 0; kc < nk && ok; ++kc) {
-          ok = mbar_wait(&empty_bar[stage], phase ^ 1u, abortp, t0);
+          {
+            TC_T0();
+            ok = mbar_wait(&empty_bar[stage], phase ^ 1u, abortp, t0);
+            TC_ADD(0);
+          }
           if (!ok) break;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)STAGE);
-          uint8_t* const sA = smem + (size_t)stage * STAGE;
-          uint8_t* const sB = sA + S * A_TILE;
+          if (skip & 1) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)STAGE);
+            uint8_t* const sA = smem + (size_t)stage * STAGE;
+            uint8_t* const sB = sA + S * A_TILE;
 #pragma unroll
-          for (int p = 0; p < S; ++p) tma_load_2d(&mapA, &full_bar[stage], sA + p * A_TILE, kc * BK, p * g.ld_pad + rowA);
+            for (int p = 0; p < S; ++p) tma_load_2d(&mapA, &full_bar[stage], sA + p * A_TILE, kc * BK, p * g.ld_pad + rowA);
 #pragma unroll
-          for (int p = 0; p < S; ++p) tma_load_2d(&mapB, &full_bar[stage], sB + p * B_TILE, kc * BK, p * g.ld_pad + rowB);
+            for (int p = 0; p < S; ++p) tma_load_2d(&mapB, &full_bar[stage], sB + p * B_TILE, kc * BK, p * g.ld_pad + rowB);
+          }
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
         if (!ok) break;
       }
+      if (DBG && g.dbg_time) atomicAdd(&g.dbg_time[0], (unsigned long long)tc_acc[0]);   // producer: waiting for a free stage
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==========================================
@@ -224,26 +251,42 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
-        // the epilogue has drained the accumulators of the previous tile
-        if (!mbar_wait(&tmem_empty_bar, tphase ^ 1u, abortp, t0)) break;
+        {   // the epilogue has drained the accumulators of the previous tile
+          TC_T0();
+          const bool okt = mbar_wait(&tmem_empty_bar, tphase ^ 1u, abortp, t0);
+          TC_ADD(0);
+          if (!okt) break;
+        }
         tcgen05_fence_after();
         bool ok = true;
         for (int kc = 0; kc < nk; ++kc) {
-          ok = mbar_wait(&full_bar[stage], phase, abortp, t0);
+          {
+            TC_T0();
+            ok = mbar_wait(&full_bar[stage], phase, abortp, t0);
+            TC_ADD(1);
+          }
           if (!ok) break;
           tcgen05_fence_after();
           const uint32_t aA = smem_u32(smem + (size_t)stage * STAGE);
           const uint32_t aB = aA + S * A_TILE;
 #pragma unroll
           for (int ks = 0; ks < BK / 32; ++ks) {
+            if (skip & 2) break;
+            // Slice p of the row block meets slices q = 0 .. S-1-p of the column block, and pair (p, q)
+            // belongs to level p+q: the B tiles of consecutive q lie back to back in shared memory
+            // (64 rows each, same row pitch) and the accumulators of consecutive levels lie side by
+            // side in TMEM, so up to four pairs go out as ONE product with N = 64 nq.  The A tile is
+            // then read from shared memory once per four pairs instead of once per pair (at N = 64 the
+            // operand reads, not the tensor pipe, set the pace: 65 clk per product measured against 32).
 #pragma unroll
             for (int p = 0; p < S; ++p) {
               const uint64_t da = umma_desc<BK>(aA + p * A_TILE + ks * 32);
 #pragma unroll
-              for (int q = 0; q < S - p; ++q) {
-                const uint64_t db = umma_desc<BK>(aB + q * B_TILE + ks * 32);
-                // level p+q; its first product of the tile (p = 0, first 32 bytes of K) overwrites
-                mma_i8(tmem_base + (uint32_t)((p + q) * kN), da, db, kInstrDesc, (kc > 0 || ks > 0 || p > 0) ? 1u : 0u);
+              for (int q0 = 0; q0 < S - p; q0 += kMaxPairs) {
+                const int nq = (S - p - q0) < kMaxPairs ? (S - p - q0) : kMaxPairs;
+                const uint64_t db = umma_desc<BK>(aB + q0 * B_TILE + ks * 32);
+                // first touch of a level in this tile: its p = 0 product over the first 32 bytes of K
+                mma_i8(tmem_base + (uint32_t)((p + q0) * kN), da, db, instr_desc(nq * kN), (kc > 0 || ks > 0 || p > 0) ? 1u : 0u);
               }
             }
           }
@@ -254,56 +297,98 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tcgen05_commit(&tmem_full_bar);        // all level sums of the tile are in TMEM
         tphase ^= 1u;
       }
+      if (DBG && g.dbg_time) {   // MMA issuer: waiting for the epilogue / for operands
+        atomicAdd(&g.dbg_time[1], (unsigned long long)tc_acc[0]);
+        atomicAdd(&g.dbg_time[2], (unsigned long long)tc_acc[1]);
+      }
     }
   } else {
-    // ================================ epilogue (4 warps, thread = row) =====================
+    // ============ epilogue: 8 warps, thread = (row, half of the tile's columns) ============
     const int quad = warp & 3;                 // a warp reaches TMEM lanes 32 (warp % 4) .. +31 only
+    const int half = (warp - 2) >> 2;          // warps 2-5: columns 0-31, warps 6-9: columns 32-63
     const int r = 32 * quad + lane;
+    constexpr int NC = kN / 2;                 // columns per thread
     uint32_t fphase = 0;
     for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
       int mbl, nbl;
       decode_tile(t, mbl, nbl);
-      const int row = g.c1 + mbl * kM + r, col0 = g.c1 + nbl * kN;
+      const int row = g.c1 + mbl * kM + r, col0 = g.c1 + nbl * kN + half * NC;
       const bool row_ok = row < g.ld;
       double* const Arow = g.A + (size_t)col0 * g.ld + row;
       const double srow = row_ok ? __ldg(g.scale + row) : 0.0;
-      // pull the tile of A towards L2 while the products run (two 128-byte lines per warp and column)
-      if (row_ok && (lane & 15) == 0) {
-#pragma unroll 8
-        for (int c = 0; c < kN; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(Arow + (size_t)c * g.ld));
+      // The thread's entries of A are fetched NOW, while the products of the tile run (a load - update -
+      // store pass behind the products had 16 loads per thread in flight and took 20,000 clocks per
+      // tile); entries above the diagonal are neither read nor written.
+      double a[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a[c] = (row_ok && row >= col0 + c && !(skip & (4 | 16))) ? __ldcg(Arow + (size_t)c * g.ld) : 0.0;
+      bool ok;
+      {
+        TC_T0();
+        ok = __all_sync(0xffffffffu, mbar_wait(&tmem_full_bar, fphase, abortp, t0));   // (tcgen05.ld is warp-collective)
+        TC_ADD(0);
       }
-      const bool ok = __all_sync(0xffffffffu, mbar_wait(&tmem_full_bar, fphase, abortp, t0));   // (tcgen05.ld is warp-collective)
       tcgen05_fence_after();
-      if (ok) {
-#pragma unroll 1
-        for (int c8 = 0; c8 < kN / 8; ++c8) {
-          double a[8];
+      const long long tc_p1__ = DBG && g.dbg_time ? clock64() : 0;
+      // Drain (holds TMEM): the S level sums of the row, 8 columns at a time -- the loads of the next 8
+      // columns are in flight while these are combined in FP64 by Horner in 2^-7 from the smallest level
+      // up (exact scalings, one rounding per level) and folded into A:
+      // A[row, col] -= 2^(e_row + e_col - 12) v.  INT32 -> FP64 goes through the 2^52 trick (LOP + DADD on
+      // the FP64 pipe) instead of I2F.
+      if (ok && !(skip & 4)) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)(half * NC);
+        int acc[2][S][8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) a[c] = (row_ok && row >= col0 + c8 * 8 + c) ? __ldcg(Arow + (size_t)(c8 * 8 + c) * g.ld) : 0.0;
-          int acc[S][8];
+        for (int l = 0; l < S; ++l) tmem_ld8(taddr + (uint32_t)(l * kN), acc[0][l]);
 #pragma unroll
-          for (int l = 0; l < S; ++l) tmem_ld8(tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)(l * kN + c8 * 8), acc[l]);
+        for (int c8 = 0; c8 < NC / 8; ++c8) {
+          double sc[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sc[c] = __ldg(g.scale + col0 + c8 * 8 + c) * srow;   // exact: powers of two
           tmem_ld_wait();
-          if (g.dbg_ld > 0 && row_ok) {
+          if (c8 + 1 < NC / 8) {
+#pragma unroll
+            for (int l = 0; l < S; ++l) tmem_ld8(taddr + (uint32_t)(l * kN + (c8 + 1) * 8), acc[(c8 + 1) & 1][l]);
+          }
+          if (DBG && g.dbg_ld > 0 && row_ok) {
 #pragma unroll
             for (int l = 0; l < S; ++l)
 #pragma unroll
-              for (int c = 0; c < 8; ++c) g.dbg_acc[((size_t)l * g.ld_pad + row) * g.dbg_ld + (col0 + c8 * 8 + c)] = acc[l][c];
+              for (int c = 0; c < 8; ++c) g.dbg_acc[((size_t)l * g.ld_pad + row) * g.dbg_ld + (col0 + c8 * 8 + c)] = acc[c8 & 1][l][c];
           }
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            double v = 0.0;
+            double h = 0.0;
+            if (skip & 8) {   // (microbenchmark: drain only)
+              int x = 0;
 #pragma unroll
-            for (int l = S - 1; l >= 0; --l) v = v * 0.0078125 + (double)acc[l][c];   // Horner in 2^-7, smallest level first
-            const int col = col0 + c8 * 8 + c;
-            if (row_ok && row >= col) Arow[(size_t)(c8 * 8 + c) * g.ld] = a[c] - (v * srow) * __ldg(g.scale + col);
+              for (int l = 0; l < S; ++l) x ^= acc[c8 & 1][l][c];
+              h = __hiloint2double(x, x);
+            } else {
+#pragma unroll
+              for (int l = S - 1; l >= 0; --l) h = h * 0.0078125 + int_to_double(acc[c8 & 1][l][c]);
+            }
+            a[c8 * 8 + c] -= h * sc[c];
           }
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar);
+      mbar_arrive(&tmem_empty_bar);   // the next tile's products may overwrite the accumulators now
       fphase ^= 1u;
       if (!ok) break;
+      const long long tc_p2__ = DBG && g.dbg_time ? clock64() : 0;
+      tc_acc[1] += tc_p2__ - tc_p1__;
+      if (!(skip & (4 | 16))) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (row_ok && row >= col0 + c) Arow[(size_t)c * g.ld] = a[c];
+      }
+      if (DBG && g.dbg_time) tc_acc[2] += clock64() - tc_p2__;
+    }
+    if (DBG && g.dbg_time && threadIdx.x == 64) {   // epilogue (one thread's view): waiting for the products / drain + combine / stores
+      atomicAdd(&g.dbg_time[3], (unsigned long long)tc_acc[0]);
+      atomicAdd(&g.dbg_time[4], (unsigned long long)tc_acc[1]);
+      atomicAdd(&g.dbg_time[5], (unsigned long long)tc_acc[2]);
     }
   }
 
@@ -436,35 +521,40 @@ inline int syrk_stages() {
   return st;
 }
 
-template <int S, int BK>
+template <int S, int BK, bool DBG>
 inline cudaError_t launch_syrk_t(const CUtensorMap& mapA, const CUtensorMap& mapB, SyrkArgs g, int grid, cudaStream_t st) {
   static bool attr_set = false;
   g.stages = syrk_stages<S, BK>();
   if (g.stages < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)g.stages * syrk_stage_bytes<S, BK>() + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ozaki_syrk_kernel<S, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ozaki_syrk_kernel<S, BK, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  ozaki_syrk_kernel<S, BK><<<grid, kThreads, smem, st>>>(mapA, mapB, g);
+  ozaki_syrk_kernel<S, BK, DBG><<<grid, kThreads, smem, st>>>(mapA, mapB, g);
   return cudaGetLastError();
+}
+template <int S, int BK>
+inline cudaError_t launch_syrk_d(const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st) {
+  if (g.dbg_acc || g.dbg_time || g.dbg_skip) return launch_syrk_t<S, BK, true>(mapA, mapB, g, grid, st);
+  return launch_syrk_t<S, BK, false>(mapA, mapB, g, grid, st);
 }
 
 inline cudaError_t launch_syrk(int S, int bk, const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st) {
   if (bk == 128) {
     switch (S) {
-      case 4: return launch_syrk_t<4, 128>(mapA, mapB, g, grid, st);
-      case 5: return launch_syrk_t<5, 128>(mapA, mapB, g, grid, st);
-      case 6: return launch_syrk_t<6, 128>(mapA, mapB, g, grid, st);
-      case 7: return launch_syrk_t<7, 128>(mapA, mapB, g, grid, st);
+      case 4: return launch_syrk_d<4, 128>(mapA, mapB, g, grid, st);
+      case 5: return launch_syrk_d<5, 128>(mapA, mapB, g, grid, st);
+      case 6: return launch_syrk_d<6, 128>(mapA, mapB, g, grid, st);
+      case 7: return launch_syrk_d<7, 128>(mapA, mapB, g, grid, st);
     }
   } else if (bk == 64) {
     switch (S) {
-      case 4: return launch_syrk_t<4, 64>(mapA, mapB, g, grid, st);
-      case 5: return launch_syrk_t<5, 64>(mapA, mapB, g, grid, st);
-      case 6: return launch_syrk_t<6, 64>(mapA, mapB, g, grid, st);
-      case 7: return launch_syrk_t<7, 64>(mapA, mapB, g, grid, st);
+      case 4: return launch_syrk_d<4, 64>(mapA, mapB, g, grid, st);
+      case 5: return launch_syrk_d<5, 64>(mapA, mapB, g, grid, st);
+      case 6: return launch_syrk_d<6, 64>(mapA, mapB, g, grid, st);
+      case 7: return launch_syrk_d<7, 64>(mapA, mapB, g, grid, st);
     }
   }
   return cudaErrorInvalidValue;

@@ -345,7 +345,11 @@ class DeviceProblem(object):
                          ("PYSFM_B200_STRICT_FLAGS", _lib.BA_OPT_STRICT_FLAGS),
                          ("PYSFM_B200_DIST_SOLVE_MIN_TILES", _lib.BA_OPT_DIST_SOLVE_MIN_TILES),
                          ("PYSFM_B200_DIST_BAND", _lib.BA_OPT_DIST_BAND),
-                         ("PYSFM_B200_SOLVER_PROFILE", _lib.BA_OPT_SOLVER_PROFILE)):
+                         ("PYSFM_B200_SOLVER_PROFILE", _lib.BA_OPT_SOLVER_PROFILE),
+                         ("PYSFM_B200_TC_MIN_TILES", _lib.BA_OPT_TC_MIN_TILES),
+                         ("PYSFM_B200_TC_SLICES", _lib.BA_OPT_TC_SLICES),
+                         ("PYSFM_B200_TC_WINDOW", _lib.BA_OPT_TC_WINDOW),
+                         ("PYSFM_B200_TC_BK", _lib.BA_OPT_TC_BK)):
             if os.environ.get(env):
                 self.set_option(opt, float(os.environ[env]))
 

@@ -3,6 +3,7 @@
 //   tc_bench syrk  [ld] [window] [slices] [bk]     one trailing update on a random panel: INT8 digits, scales and the
 //                                                  right-hand side against a host restatement (digits bit for bit), the raw
 //                                                  INT32 level sums out of TMEM bit for bit, the updated matrix bit for bit
+//   tc_bench perf  [ld] [window] [slices] [bk] [reps] [skip]   time of one trailing update at a given size (no verification)
 //   tc_bench solve [n_opt_cam] [window] [slices] [bk] [reps]
 //                                                  random SPD system: blocked tcgen05 solve against the DMMA dataflow
 //                                                  solve (same library code path as ba_solve): solutions, residuals, times
@@ -240,11 +241,56 @@ static int run_solve(int nc, int w, int S, int bk, int reps) {
   return bad;
 }
 
+// ---------------------------------------------------------------------------------------------
+// time of one trailing update (slices + products) at a given size, no verification
+static int run_perf(int ld, int w, int S, int bk, int reps, int skip) {
+  const int K = 64 * w;
+  ba::Context c;
+  alloc_context(c, 64);
+  c.ld = ld;
+  cudaFree(c.Adense); CK(cudaMalloc(&c.Adense, ((size_t)ld * ld + ld) * 8));
+  c.tc_window = w; c.tc_slices_n = S; c.tc_bk = bk; c.tc_min_tiles = 1; c.tc_dbg_skip = skip;
+  CK(ba::tc_prepare(c));
+  {
+    std::vector<double> col((size_t)ld);
+    srand(3);
+    for (int q = 0; q <= K; ++q) {   // the panel columns (and the right-hand side behind the matrix)
+      for (int p = 0; p < ld; ++p) col[p] = urand();
+      CK(cudaMemcpy(q < K ? c.Adense + (size_t)q * ld : c.Adense + (size_t)ld * ld, col.data(), (size_t)ld * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  CK(cudaMalloc(&c.tc_dbg_time, 8 * 8)); CK(cudaMemset(c.tc_dbg_time, 0, 64));
+  cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  const int n_nb = (ld - K) / 64, ntiles = ba::tc::count_tiles(n_nb);
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0));
+    CK(ba::launch_tc_trailing_update(c, c.Adense, c.Adense + (size_t)ld * ld, 0, nullptr, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  const double flops = (double)(ld - K) * (ld - K) * K;   // lower triangle: m^2/2 * K * 2
+  ba::Scalars sc; CK(cudaMemcpy(&sc, c.scalars, sizeof sc, cudaMemcpyDeviceToHost));
+  printf("perf: skip %d ld %d K %d S %d bk %d: slices + update %.3f ms (best of %d), %d tiles of 128x64 -> %.2f us per tile per SM, %.1f TFLOP/s FP64-equivalent, status %g\n",
+         skip, ld, K, S, bk, best, reps, ntiles, best * 1e3 / ((ntiles + c.num_sms - 1) / c.num_sms), flops / (best * 1e-3) / 1e12, sc.status);
+  {
+    unsigned long long tm[8];
+    CK(cudaMemcpy(tm, c.tc_dbg_time, 64, cudaMemcpyDeviceToHost));
+    const double per = 1.0 / ((double)ntiles * reps);   // clocks per tile
+    printf("      clocks per tile: producer waits for a stage %.0f | MMA issuer waits for the epilogue %.0f, for operands %.0f | epilogue waits for the products %.0f, drains + combines %.0f, updates A %.0f\n",
+           tm[0] * per, tm[1] * per, tm[2] * per, tm[3] * per, tm[4] * per, tm[5] * per);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "syrk";
   auto arg = [&](int i, int d) { return argc > i ? atoi(argv[i]) : d; };
   if (!strcmp(mode, "syrk")) return run_syrk(arg(2, 640), arg(3, 2), arg(4, 6), arg(5, 64));
   if (!strcmp(mode, "solve")) return run_solve(arg(2, 199), arg(3, 8), arg(4, 6), arg(5, 64), arg(6, 3));
-  printf("usage: tc_bench syrk|solve ...\n");
+  if (!strcmp(mode, "perf")) return run_perf(arg(2, 12032), arg(3, 8), arg(4, 6), arg(5, 64), arg(6, 3), arg(7, 0));
+  printf("usage: tc_bench syrk|solve|perf ...\n");
   return 2;
 }
