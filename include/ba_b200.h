@@ -80,7 +80,7 @@ enum {
   BA_OPT_TC_MIN_TILES = 7,         /* ba_solve takes the blocked factorisation whose trailing updates run as INT8
                                       products on tcgen05 (Ozaki slices of the FP64 panel, exact INT32 sums in
                                       tensor memory, FP64 recombination) when the reduced system has at least this
-                                      many 64-wide tile rows and is not solved distributed (default 96, i.e. >= 1024
+                                      many 64-wide tile rows and is not solved distributed (default 80, i.e. >= 854
                                       cameras; 0 = never: FP64 DMMA only) */
   BA_OPT_TC_SLICES = 8,            /* INT8 slices per FP64 operand, 4 .. 7 (default 6: trailing updates to 2^-42 of
                                       the row scales; 7 = FP64 level; each step fewer is ~25 % faster and 128x coarser) */
@@ -282,6 +282,26 @@ int ba_sync(ba_handle h, void* stream);
  * [7] waiting for y_k, [8] backward-substitution waits, [9] start barrier, [10] whole launch,
  * [11] chain tasks, [12] diagonal-update tasks.  Needs BA_OPT_SOLVER_PROFILE = 1.  Synchronises. */
 int ba_solver_profile(ba_handle h, unsigned long long* out16_host, int reset, void* stream);
+
+/* Test entry of the tcgen05 trailing update that the blocked factorisation of large reduced
+ * systems (BA_OPT_TC_MIN_TILES) applies after every panel -- one step of the Cholesky behind
+ * solve_motion_normal_eqns (bundle_adjuster.py:281-312, numpy.linalg.solve there).  Stateless;
+ * everything lives in HOST memory; synchronises.  A_host is a dense [ld x ld] column-major matrix
+ * whose first K = 64 * window columns hold a factored panel L; the call performs, on the device,
+ *     A[i, j] -= sum_k L[i, k] L[j, k]      for K <= j <= i < ld   (lower triangle of the trailing block)
+ *     rhs[i]  -= sum_k L[i, k] rhs[k]        for K <= i < ld        (rows K .. K+63 start from saved_rhs
+ *                                                                   when it is not NULL)
+ * through `slices` (4 .. 7) signed 7-bit INT8 digit planes per FP64 entry, exact INT32 level sums
+ * on the tensor cores, FP64 recombination (ba_solve_tc.cuh).  Optional outputs expose every integer
+ * intermediate so that a CPU restatement can be held to it bit for bit:
+ *   digits_host     [slices][ld_pad][K]  (ld_pad = ld rounded up to 128; rows < K are not written)
+ *   scale_host      [ld_pad]             2^(e_i - 6), x_ik = L_ik 2^-e_i in (-1, 1)
+ *   level_sums_host [slices][ld_pad][ld] sum over p + q = level, k of digit_p[i, k] digit_q[j, k]
+ * ld: multiple of 64, > K; window even, 2 .. 16; bk 64 or 128.  Returns BA_ERR_TIMEOUT if a wait
+ * inside the kernel ran past its deadline. */
+int ba_tc_trailing_update_host(int device, int ld, int window, int slices, int bk, double* A_host,
+                               double* rhs_host, const double* saved_rhs_host,
+                               signed char* digits_host, double* scale_host, int* level_sums_host);
 
 /* Number of kernel launches issued through this handle since creation (bench evidence). */
 long long ba_launch_count(ba_handle h);

@@ -584,4 +584,53 @@ int ba_solver_profile(ba_handle h, unsigned long long* out16, int reset, void* s
 
 long long ba_launch_count(ba_handle h) { return h ? h->launches : 0; }
 
+int ba_tc_trailing_update_host(int device, int ld, int window, int slices, int bk, double* A_host, double* rhs_host,
+                               const double* saved_rhs_host, signed char* digits_host, double* scale_host, int* level_sums_host) {
+  if (ld < 128 || (ld % 64) != 0 || !A_host || !rhs_host || ld <= 64 * window) return BA_ERR_BAD_ARGUMENT;
+  DeviceGuard guard__(device);
+  ba::Context c;   // a scratch context: only the solver workspace of the trailing update exists
+  c.device = device;
+  c.ld = ld;
+  c.tc_window = window; c.tc_slices_n = slices; c.tc_bk = bk;
+  cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t ld_pad = ((size_t)ld + 127) / 128 * 128, K = (size_t)64 * window;
+  const size_t dense = (size_t)ld * ld + ld;
+  int rc = BA_OK;
+  bool ok = dev_alloc(&c.Adense, dense) == cudaSuccess && dev_alloc(&c.scalars, 1) == cudaSuccess &&
+            dev_alloc(&c.solve_abort, 2) == cudaSuccess &&
+            cudaMemset(c.scalars, 0, sizeof(ba::Scalars)) == cudaSuccess && cudaMemset(c.solve_abort, 0, 8) == cudaSuccess &&
+            ba::tc_prepare(c) == cudaSuccess;
+  if (ok && level_sums_host) {
+    ok = dev_alloc(&c.tc_dbg, (size_t)slices * ld_pad * ld) == cudaSuccess &&
+         cudaMemset(c.tc_dbg, 0, (size_t)slices * ld_pad * ld * sizeof(int)) == cudaSuccess;
+    c.tc_dbg_ld = ld;
+  }
+  if (ok) {
+    ok = cudaMemcpy(c.Adense, A_host, (size_t)ld * ld * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(c.Adense + (size_t)ld * ld, rhs_host, (size_t)ld * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && saved_rhs_host) ok = cudaMemcpy(c.tc_save, saved_rhs_host, 64 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  if (ok) {
+    ok = ba::launch_tc_trailing_update(c, c.Adense, c.Adense + (size_t)ld * ld, 0, saved_rhs_host ? c.tc_save : nullptr, 0) == cudaSuccess &&
+         cudaDeviceSynchronize() == cudaSuccess;
+  }
+  if (ok) {
+    ba::Scalars sc;
+    ok = cudaMemcpy(&sc, c.scalars, sizeof sc, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(A_host, c.Adense, (size_t)ld * ld * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(rhs_host, c.Adense + (size_t)ld * ld, (size_t)ld * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && digits_host) ok = cudaMemcpy(digits_host, c.tc_slices, (size_t)slices * ld_pad * K, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && scale_host) ok = cudaMemcpy(scale_host, c.tc_scale, ld_pad * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && level_sums_host)
+      ok = cudaMemcpy(level_sums_host, c.tc_dbg, (size_t)slices * ld_pad * ld * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && sc.status != 0.0) rc = BA_ERR_TIMEOUT;
+  }
+  if (!ok) rc = (rc == BA_OK) ? BA_ERR_CUDA : rc;
+  void* ptrs[] = {c.Adense, c.scalars, c.solve_abort, c.tc_slices, c.tc_scale, c.tc_save, c.tc_dbg};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (rc == BA_ERR_CUDA) cudaGetLastError();
+  return rc;
+}
+
 }  // extern "C"

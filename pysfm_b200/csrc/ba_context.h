@@ -147,7 +147,7 @@ struct Context {
   int solve_grid_cap = 0;                   // BA_OPT_SOLVE_GRID_CAP: at most this many solver CTAs (0 = one per SM)
   int split_min_tiles = 32;                 // diagonal-update tasks take over part of the chain tasks from this many tile rows on
   // blocked solve with the tcgen05 trailing update (ba_solve_tc.cuh; single-GPU handles, large systems)
-  int tc_min_tiles = 0;                     // BA_OPT_TC_MIN_TILES: tile rows from which ba_solve takes this path (0 = never)
+  int tc_min_tiles = 80;                    // BA_OPT_TC_MIN_TILES: tile rows from which ba_solve takes this path (0 = never)
   int tc_slices_n = 6;                      // BA_OPT_TC_SLICES: INT8 slices per FP64 operand (4 .. 7)
   int tc_window = 8;                        // BA_OPT_TC_WINDOW: tile columns per panel (even, <= 16): K = 64 * window
   int tc_bk = 64;                           // BA_OPT_TC_BK: bytes of K per pipeline stage = swizzle span (64 or 128)
@@ -181,6 +181,8 @@ cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
 bool tc_solve_selected(const Context& c);
+cudaError_t tc_prepare(Context& c);   // slice buffers + tensor maps for (c.ld, tc_slices_n, tc_window, tc_bk)
+cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0, const double* saved_rhs, cudaStream_t st);
 bool dist_solve_selected(const Context& c);
 
 }  // namespace ba

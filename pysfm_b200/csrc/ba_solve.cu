@@ -1705,7 +1705,7 @@ bool tc_solve_selected(const Context& c) {
   return c.tc_min_tiles > 0 && c.ld / NB >= c.tc_min_tiles && c.ld / NB > c.tc_window + 1 && !dist_solve_selected(c);
 }
 
-static cudaError_t tc_prepare(Context& c) {
+cudaError_t tc_prepare(Context& c) {
   const int ld = c.ld, w = c.tc_window, K = NB * w, S = c.tc_slices_n;
   if (c.tc_slices && c.tc_cfg[0] == S && c.tc_cfg[1] == w && c.tc_cfg[2] == c.tc_bk && c.tc_cfg[3] == ld) return cudaSuccess;
   if (S < 4 || S > 7 || w < 2 || w > tc::kMaxWindowTiles || (w & 1) || (c.tc_bk != 64 && c.tc_bk != 128)) return cudaErrorInvalidValue;

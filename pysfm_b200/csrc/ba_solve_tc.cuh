@@ -30,7 +30,7 @@
 //   ozaki_syrk_kernel       A22 -= L21 L21^T, lower triangle, 128 x 64 tiles, persistent,
 //                           warp-specialised: TMA producer / MMA issuer / 4 epilogue warps  [tcgen05]
 //
-// Accuracy (oracle/ozaki_model.py restates the arithmetic in numpy; tests/test_ozaki_model.py):
+// Accuracy (tests/test_ozaki_model.py holds a numpy restatement of this arithmetic to FP64):
 // S = 6 reproduces the FP64 solve of BA reduced systems to ~1e-11 relative at condition 1e4
 // (S = 5: 1e-9, S = 7: FP64 level); the int8 slices and INT32 level sums are bit-exact by
 // construction and are tested as such against the numpy model on the GPU.
