@@ -364,8 +364,12 @@ def run_c4(args, dev, world, rank):
                "steps": steps, "stages_ms": stage_ms, "gpu_launches": int(launches),
                "reduced_system": "%d x %d" % (n, n),
                "solve": ("distributed tile Cholesky over peer memory (fused reduce-scatter + factor + all-gather of L, ba_solve.cu DIST)"
-                         if h.prob.dist_solve else "replicated on every rank" if world > 1 else "single GPU"),
+                         if h.prob.dist_solve else
+                         "blocked Cholesky: panels on FP64 DMMA, trailing updates as exact INT8 products on tcgen05 (Ozaki slices of the "
+                         "FP64 panel, INT32 level sums in TMEM, TMA-fed; ba_solve_tc.cuh)" + (", replicated on every rank" if world > 1 else "")
+                         if h.prob.tc_solve_active() else "replicated on every rank" if world > 1 else "single GPU, FP64 DMMA dataflow kernel"),
                "solve_fp64_tflops": n ** 3 / 3.0 / (stage_ms["solve"] * 1e-3) / 1e12,
+               "solve_fp64_tflops_note": "n^3/3 FP64-equivalent flops over the solve stage (expand + factor + substitutions)",
                "fp64_tflops_peak_per_gpu": FP64_PEAK_TFLOPS,
                "final": {"cost": cost, "cand_cost": cand, "solve_status": status},
                "parity": par, "setup_s": setup_s, "oracle_cpu_s_per_step": float(g["seconds"])}

@@ -234,6 +234,13 @@ int ba_allreduce_costs(ba_handle h, void* stream);
  * All ranks must then call ba_solve collectively. */
 int ba_dist_solve_active(ba_handle h);
 
+/* 1 when ba_solve on this handle, as configured now, takes the blocked factorisation whose trailing
+ * updates run on tcgen05 (BA_OPT_TC_MIN_TILES; large reduced systems that are not solved
+ * distributed), 0 when it runs the FP64 dataflow kernel alone.  Both solve the same system
+ * (solve_motion_normal_eqns, bundle_adjuster.py:281-312); they differ by the slice truncation
+ * documented at BA_OPT_TC_SLICES. */
+int ba_tc_solve_active(ba_handle h);
+
 /* Per-observation residuals and Jacobians of the current state (bundle.py:251, :255-277),
  * for Bundle.residuals()/Jresiduals() and stage-wise parity checks. */
 int ba_eval_observations(ba_handle h, void* stream);

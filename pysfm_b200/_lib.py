@@ -52,6 +52,7 @@ SIGNATURES = {
     "ba_get_system": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
     "ba_set_option": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double]),
     "ba_dist_solve_active": (ctypes.c_int, [_vp]),
+    "ba_tc_solve_active": (ctypes.c_int, [_vp]),
     "ba_linearize_eliminate": (ctypes.c_int, [_vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _vp]),
     "ba_solve": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_backsub_retract_cost": (ctypes.c_int, [_vp, _vp]),

@@ -366,6 +366,11 @@ int ba_dist_solve_active(ba_handle h) {
   return ba::dist_solve_selected(probe) ? 1 : 0;
 }
 
+int ba_tc_solve_active(ba_handle h) {
+  if (!h) return 0;
+  return ba::tc_solve_selected(*h) ? 1 : 0;
+}
+
 int ba_linearize_eliminate(ba_handle h, double damping, double pinv_rcond, int flags, void* stream) {
   if (!h) return BA_ERR_BAD_ARGUMENT;
   if (!bound(*h) || ((flags & BA_WANT_SCHUR) && !h->sys)) return BA_ERR_NOT_BOUND;

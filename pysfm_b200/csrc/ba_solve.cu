@@ -1784,7 +1784,10 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
   g.x = c.dC;
   for (int j0 = 0; j0 < T; j0 += w) {
     const int Tw = T - j0;                       // tile rows of the trailing matrix
-    const bool last = Tw <= w + 1;               // what is left is one window: factor it all
+    // What is left is one window, or small enough that the dataflow kernel alone is faster on it
+    // (below ~80 tile rows a panel leaves most SMs idle behind the chain and the trailing update has
+    // fewer tiles than SMs): factor it all in this launch.
+    const bool last = Tw <= w + 1 || (j0 > 0 && Tw < c.tc_min_tiles);
     const int c0 = j0 * NB;
     // tickets of the leading w tile columns: C_0, then per column jc < w the T' - jc tasks D_{jc+1}, C_{jc+1}, (jc+2.., jc)
     const int ntasks = last ? 1 + (Tw - 1) * (Tw + 2) / 2 : 1 + w * Tw - w * (w - 1) / 2;
@@ -1799,7 +1802,7 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
     g.epoch = ++c.solve_epoch;
     g.phase = kPhaseWindow;
     g.window_tasks = ntasks;
-    g.split = 0;
+    g.split = last && Tw >= c.split_min_tiles;   // (windows have k loops of at most w steps: nothing to hand over)
     g.prof = nullptr;
     int grid = ntasks < c.num_sms ? ntasks : c.num_sms;
     if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;

@@ -408,23 +408,25 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // Row scales, S INT8 slice matrices (K-major: slices[p][row][k], row pitch K bytes) of the panel
 // L[c1.., c0..c1) and the right-looking update of the right-hand side, b[row] -= sum_k L[row,k] y[k].
-// One CTA per 64 rows; thread = (row r, quarter g of the columns).
+// One CTA per 16 rows (720 CTAs at 2,000 cameras: the kernel lives on loads in flight, not on
+// arithmetic); thread = (row r, one of 16 column groups).
+constexpr int kSliceRows = 16;
 template <int S>
 __global__ void __launch_bounds__(256)
 slice_panel_kernel(const double* __restrict__ A, int ld, int c0, int K, double* __restrict__ rhs,
                    const double* __restrict__ saved_rhs, int8_t* __restrict__ slices, size_t slice_stride,
                    double* __restrict__ scale) {
   __shared__ double s_y[64 * kMaxWindowTiles];
-  __shared__ double s_mx[4][64], s_dot[4][64], s_mul[64];
-  const int tid = threadIdx.x, r = tid & 63, gq = tid >> 6;
-  const int c1 = c0 + K, R0 = c1 + 64 * blockIdx.x;
+  __shared__ double s_mx[16][kSliceRows], s_dot[16][kSliceRows], s_mul[kSliceRows];
+  const int tid = threadIdx.x, r = tid & (kSliceRows - 1), gq = tid / kSliceRows;
+  const int c1 = c0 + K, R0 = c1 + kSliceRows * blockIdx.x;
   for (int k = tid; k < K; k += 256) s_y[k] = rhs[c0 + k];   // y of the window (written by its chain tasks)
   __syncthreads();
   const double* const col = A + (size_t)c0 * ld + R0 + r;
   {
     double mx = 0.0, dot = 0.0;
 #pragma unroll 8
-    for (int k = gq; k < K; k += 4) {
+    for (int k = gq; k < K; k += 16) {
       const double v = __ldcg(col + (size_t)k * ld);
       mx = fmax(mx, fabs(v));
       dot = fma(v, s_y[k], dot);
@@ -433,20 +435,26 @@ slice_panel_kernel(const double* __restrict__ A, int ld, int c0, int K, double* 
     s_dot[gq][r] = dot;
   }
   __syncthreads();
-  if (tid < 64) {
-    const double mx = fmax(fmax(s_mx[0][r], s_mx[1][r]), fmax(s_mx[2][r], s_mx[3][r]));
-    const double dot = (s_dot[0][r] + s_dot[1][r]) + (s_dot[2][r] + s_dot[3][r]);
+  if (tid < kSliceRows) {
+    double mx = 0.0, dot = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      mx = fmax(mx, s_mx[q][r]);
+      dot += s_dot[q][r];
+    }
     // |x| 2^-e < 1  (mx = f 2^e, f in [0.5, 1));  non-finite rows (a failed pivot upstream) get e = 0
     const int e = (mx > 0.0 && mx < 1.7e308) ? ilogb(mx) + 1 : 0;
     s_mul[r] = scalbn(1.0, 6 - e);
     scale[R0 + r] = scalbn(1.0, e - 6);
     // the tile row right below the window: its b was saved before the window launch overwrote it
-    const double b = (blockIdx.x == 0 && saved_rhs) ? saved_rhs[r] : rhs[R0 + r];
+    const int below = R0 + r - c1;
+    const double b = (below < 64 && saved_rhs) ? saved_rhs[below] : rhs[R0 + r];
     rhs[R0 + r] = b - dot;
   }
   __syncthreads();
   const double mul = s_mul[r];
-  for (int kc = 0; kc < K; kc += 64) {
+  for (int kc = 0; kc < K; kc += 256) {
+    if (kc + 16 * gq >= K) break;   // (K is a multiple of 64, not of 256: whole 16-column groups fall in or out)
     double v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __ldcg(col + (size_t)(kc + 16 * gq + i) * ld) * mul;
@@ -562,7 +570,7 @@ inline cudaError_t launch_syrk(int S, int bk, const CUtensorMap& mapA, const CUt
 
 inline cudaError_t launch_slice(int S, const double* A, int ld, int c0, int K, double* rhs, const double* saved_rhs, int8_t* slices,
                                 size_t slice_stride, double* scale, cudaStream_t st) {
-  const int blocks = (ld - (c0 + K)) / 64;
+  const int blocks = (ld - (c0 + K)) / kSliceRows;
   if (blocks <= 0) return cudaSuccess;
   switch (S) {
     case 4: slice_panel_kernel<4><<<blocks, 256, 0, st>>>(A, ld, c0, K, rhs, saved_rhs, slices, slice_stride, scale); break;

@@ -615,5 +615,9 @@ class DeviceProblem(object):
                   "ba_solver_profile")
         return dict((name, out[i] * 1e-6) for i, name in enumerate(_lib.SOLVER_PROFILE_SLOTS))
 
+    def tc_solve_active(self):
+        """True when ba_solve takes the blocked path with tcgen05 trailing updates (BA_OPT_TC_MIN_TILES)."""
+        return bool(self.lib.ba_tc_solve_active(self.h))
+
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))
