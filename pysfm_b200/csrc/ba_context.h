@@ -158,6 +158,7 @@ struct Context {
   int tc_dbg_ld = 0;
   unsigned long long* tc_dbg_time = nullptr;  // microbenchmarks: role timers of the trailing-update kernel (SyrkArgs::dbg_time)
   int tc_dbg_skip = 0;                      // microbenchmarks: roles of the trailing-update kernel switched off (SyrkArgs::dbg_skip)
+  bool tc_attr_set[16] = {false, false, false, false, false, false, false, false, false, false, false, false, false, false, false, false};
   int tc_cfg[4] = {0, 0, 0, 0};             // (slices, window, bk, ld) the buffers and tensor maps were built for
   alignas(64) unsigned char tc_map_a[128];  // CUtensorMap: box 128 rows x bk bytes
   alignas(64) unsigned char tc_map_b[128];  // CUtensorMap: box  64 rows x bk bytes

@@ -1751,7 +1751,7 @@ cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0
   int grid = g.ntiles < c.num_sms ? g.ntiles : c.num_sms;
   if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
   e = tc::launch_syrk(c.tc_slices_n, c.tc_bk, *reinterpret_cast<const CUtensorMap*>(c.tc_map_a),
-                      *reinterpret_cast<const CUtensorMap*>(c.tc_map_b), g, grid, st);
+                      *reinterpret_cast<const CUtensorMap*>(c.tc_map_b), g, grid, st, c.tc_attr_set);
   c.launches += 1;
   return e;
 }

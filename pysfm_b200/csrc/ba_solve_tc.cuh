@@ -530,8 +530,9 @@ inline int syrk_stages() {
 }
 
 template <int S, int BK, bool DBG>
-inline cudaError_t launch_syrk_t(const CUtensorMap& mapA, const CUtensorMap& mapB, SyrkArgs g, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+inline cudaError_t launch_syrk_t(const CUtensorMap& mapA, const CUtensorMap& mapB, SyrkArgs g, int grid, cudaStream_t st, bool* attr_flags) {
+  // the shared-memory opt-in is a per-device attribute: remembered per handle, not per process
+  bool& attr_set = attr_flags[(S - 4) * 4 + (BK == 128 ? 2 : 0) + (DBG ? 1 : 0)];
   g.stages = syrk_stages<S, BK>();
   if (g.stages < 1) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)g.stages * syrk_stage_bytes<S, BK>() + 1024;
@@ -544,25 +545,26 @@ inline cudaError_t launch_syrk_t(const CUtensorMap& mapA, const CUtensorMap& map
   return cudaGetLastError();
 }
 template <int S, int BK>
-inline cudaError_t launch_syrk_d(const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st) {
-  if (g.dbg_acc || g.dbg_time || g.dbg_skip) return launch_syrk_t<S, BK, true>(mapA, mapB, g, grid, st);
-  return launch_syrk_t<S, BK, false>(mapA, mapB, g, grid, st);
+inline cudaError_t launch_syrk_d(const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st, bool* attr_flags) {
+  if (g.dbg_acc || g.dbg_time || g.dbg_skip) return launch_syrk_t<S, BK, true>(mapA, mapB, g, grid, st, attr_flags);
+  return launch_syrk_t<S, BK, false>(mapA, mapB, g, grid, st, attr_flags);
 }
 
-inline cudaError_t launch_syrk(int S, int bk, const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st) {
+inline cudaError_t launch_syrk(int S, int bk, const CUtensorMap& mapA, const CUtensorMap& mapB, const SyrkArgs& g, int grid, cudaStream_t st,
+                               bool* attr_flags /* [16], per handle */) {
   if (bk == 128) {
     switch (S) {
-      case 4: return launch_syrk_d<4, 128>(mapA, mapB, g, grid, st);
-      case 5: return launch_syrk_d<5, 128>(mapA, mapB, g, grid, st);
-      case 6: return launch_syrk_d<6, 128>(mapA, mapB, g, grid, st);
-      case 7: return launch_syrk_d<7, 128>(mapA, mapB, g, grid, st);
+      case 4: return launch_syrk_d<4, 128>(mapA, mapB, g, grid, st, attr_flags);
+      case 5: return launch_syrk_d<5, 128>(mapA, mapB, g, grid, st, attr_flags);
+      case 6: return launch_syrk_d<6, 128>(mapA, mapB, g, grid, st, attr_flags);
+      case 7: return launch_syrk_d<7, 128>(mapA, mapB, g, grid, st, attr_flags);
     }
   } else if (bk == 64) {
     switch (S) {
-      case 4: return launch_syrk_d<4, 64>(mapA, mapB, g, grid, st);
-      case 5: return launch_syrk_d<5, 64>(mapA, mapB, g, grid, st);
-      case 6: return launch_syrk_d<6, 64>(mapA, mapB, g, grid, st);
-      case 7: return launch_syrk_d<7, 64>(mapA, mapB, g, grid, st);
+      case 4: return launch_syrk_d<4, 64>(mapA, mapB, g, grid, st, attr_flags);
+      case 5: return launch_syrk_d<5, 64>(mapA, mapB, g, grid, st, attr_flags);
+      case 6: return launch_syrk_d<6, 64>(mapA, mapB, g, grid, st, attr_flags);
+      case 7: return launch_syrk_d<7, 64>(mapA, mapB, g, grid, st, attr_flags);
     }
   }
   return cudaErrorInvalidValue;

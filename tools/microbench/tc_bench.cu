@@ -4,7 +4,7 @@
 //                                                  right-hand side against a host restatement (digits bit for bit), the raw
 //                                                  INT32 level sums out of TMEM bit for bit, the updated matrix bit for bit
 //   tc_bench perf  [ld] [window] [slices] [bk] [reps] [skip]   time of one trailing update at a given size (no verification)
-//   tc_bench solve [n_opt_cam] [window] [slices] [bk] [reps]
+//   tc_bench solve [n_opt_cam] [window] [slices] [bk] [reps] [min_tiles]
 //                                                  random SPD system: blocked tcgen05 solve against the DMMA dataflow
 //                                                  solve (same library code path as ba_solve): solutions, residuals, times
 #include "../../pysfm_b200/csrc/ba_solve.cu"
@@ -170,7 +170,7 @@ static int run_syrk(int ld, int w, int S, int bk) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static int run_solve(int nc, int w, int S, int bk, int reps) {
+static int run_solve(int nc, int w, int S, int bk, int reps, int min_tiles) {
   const int n = 6 * nc, ld = (n + 63) / 64 * 64, T = ld / 64;
   printf("== solve: nc %d n %d T %d, window %d, slices %d, bk %d\n", nc, n, T, w, S, bk);
   const size_t nblk = (size_t)nc * (nc + 1) / 2, sys_len = nblk * 36 + n;
@@ -200,7 +200,7 @@ static int run_solve(int nc, int w, int S, int bk, int reps) {
   float best[2] = {1e30f, 1e30f};
   int bad = 0;
   for (int mode = 0; mode < 2; ++mode) {   // 0: DMMA dataflow solve, 1: blocked tcgen05 solve
-    c.tc_min_tiles = mode ? 1 : 0;
+    c.tc_min_tiles = mode ? min_tiles : 0;   // (also the size below which the tail goes to the dataflow kernel)
     if (mode && !ba::tc_solve_selected(c)) { printf("   (system too small for the blocked path)\n"); return 0; }
     for (int r = 0; r < reps; ++r) {
       CK(cudaEventRecord(e0));
@@ -289,7 +289,7 @@ int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "syrk";
   auto arg = [&](int i, int d) { return argc > i ? atoi(argv[i]) : d; };
   if (!strcmp(mode, "syrk")) return run_syrk(arg(2, 640), arg(3, 2), arg(4, 6), arg(5, 64));
-  if (!strcmp(mode, "solve")) return run_solve(arg(2, 199), arg(3, 8), arg(4, 6), arg(5, 64), arg(6, 3));
+  if (!strcmp(mode, "solve")) return run_solve(arg(2, 199), arg(3, 8), arg(4, 6), arg(5, 64), arg(6, 3), arg(7, 1));
   if (!strcmp(mode, "perf")) return run_perf(arg(2, 12032), arg(3, 8), arg(4, 6), arg(5, 64), arg(6, 3), arg(7, 0));
   printf("usage: tc_bench syrk|solve|perf ...\n");
   return 2;
