@@ -82,6 +82,17 @@ def test_hot_kernels_use_the_fp64_tensor_pipe_and_the_tma_path():
     # as plain 16-byte stores (STG.E.128), flags with system-scope stores
     assert count("chol_dataflow_kernelILb1E", "UBLKCP") >= 1
     assert count("chol_dataflow_kernelILb1E", "DMMA.8x8x4") > 100
+    # large reduced systems: the trailing update of the blocked factorisation is a Blackwell tensor
+    # kernel -- tcgen05.mma kind::i8 (UTCIMMA) fed by TMA tensor-map loads (UTMALDG), accumulators read
+    # back from tensor memory (LDTM), completion through tcgen05.commit (UTCBAR); product instantiation
+    # (DBG = false, 6 slices, 64-byte K steps): 8 merged products per 32 bytes of K, two per stage
+    prod = "ozaki_syrk_kernelILi6ELi64ELb0E"
+    assert count(prod, "UTCIMMA") == 16
+    assert count(prod, "UTMALDG.2D") == 12
+    assert count(prod, "LDTM") >= 24
+    assert count(prod, "UTCBAR") >= 2
+    assert count(prod, "STL") <= 16          # (a handful of spilled words at 168 registers, none in the product loop)
+    assert count("ozaki_syrk_kernel", "DMMA") == 0 and count("ozaki_syrk_kernel", "HMMA") == 0
 
 
 def test_no_cpu_fallback_without_cuda():
