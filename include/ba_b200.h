@@ -85,7 +85,10 @@ enum {
   BA_OPT_TC_SLICES = 8,            /* INT8 slices per FP64 operand, 4 .. 7 (default 6: trailing updates to 2^-42 of
                                       the row scales; 7 = FP64 level; each step fewer is ~25 % faster and 128x coarser) */
   BA_OPT_TC_WINDOW = 9,            /* tile columns per panel of the blocked factorisation (even, 2 .. 16; default 8) */
-  BA_OPT_TC_BK = 10                /* bytes of the contraction per pipeline stage = TMA/UMMA swizzle span (64 or 128) */
+  BA_OPT_TC_BK = 10,               /* bytes of the contraction per pipeline stage = TMA/UMMA swizzle span (64 or 128) */
+  BA_OPT_TC_OVER_DIST_MAX_WORLD = 11 /* sharded handles of at most this many ranks (default 2) prefer "all-reduce + blocked
+                                      tcgen05 solve on every rank" over the distributed solve when both qualify
+                                      (ba_dist_solve_active then answers 0); set the same value on every rank */
 };
 
 enum { BA_MODEL_GAUSSIAN = 0, BA_MODEL_CAUCHY = 1 }; /* sensor_model.py:7-32 / :37-72 */

@@ -19,7 +19,7 @@ BA_ERR_TIMEOUT = 7
 
 (BA_OPT_SPIN_TIMEOUT_MS, BA_OPT_STRICT_FLAGS, BA_OPT_DIST_SOLVE_MIN_TILES, BA_OPT_DIST_BAND,
  BA_OPT_SOLVE_GRID_CAP, BA_OPT_SOLVER_PROFILE, BA_OPT_FUSE_COST_REDUCTION,
- BA_OPT_TC_MIN_TILES, BA_OPT_TC_SLICES, BA_OPT_TC_WINDOW, BA_OPT_TC_BK) = range(11)
+ BA_OPT_TC_MIN_TILES, BA_OPT_TC_SLICES, BA_OPT_TC_WINDOW, BA_OPT_TC_BK, BA_OPT_TC_OVER_DIST_MAX_WORLD) = range(12)
 SOLVER_PROFILE_SLOTS = ["panel_tasks", "wait_k_operands", "last_step_polls", "panel_idle_rounds", "wait_diag_task",
                         "peer_flags", "peer_contributions", "wait_y", "backward_waits", "start_barrier", "launch",
                         "chain_tasks", "diag_tasks"]

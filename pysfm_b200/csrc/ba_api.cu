@@ -352,6 +352,7 @@ int ba_set_option(ba_handle h, int option, double value) {
       break;
     }
     case BA_OPT_TC_BK: if (value != 64.0 && value != 128.0) return BA_ERR_BAD_ARGUMENT; h->tc_bk = (int)value; break;
+    case BA_OPT_TC_OVER_DIST_MAX_WORLD: if (value < 0.0) return BA_ERR_BAD_ARGUMENT; h->tc_over_dist_max_world = (int)value; break;
     default: return BA_ERR_BAD_ARGUMENT;
   }
   return BA_OK;

@@ -150,6 +150,8 @@ struct Context {
   int tc_min_tiles = 80;                    // BA_OPT_TC_MIN_TILES: tile rows from which ba_solve takes this path (0 = never)
   int tc_slices_n = 6;                      // BA_OPT_TC_SLICES: INT8 slices per FP64 operand (4 .. 7)
   int tc_window = 8;                        // BA_OPT_TC_WINDOW: tile columns per panel (even, <= 16): K = 64 * window
+  int tc_over_dist_max_world = 2;           // BA_OPT_TC_OVER_DIST_MAX_WORLD: sharded handles of at most this many ranks all-reduce and run the
+                                            // blocked solve on every rank instead of the distributed solve (same value on every rank)
   int tc_bk = 64;                           // BA_OPT_TC_BK: bytes of K per pipeline stage = swizzle span (64 or 128)
   signed char* tc_slices = nullptr;         // [slices][ld_pad][64 * window] INT8 digits of the current panel, K-major
   double* tc_scale = nullptr;               // [ld_pad] power-of-two row scales of the current panel

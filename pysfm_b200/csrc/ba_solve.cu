@@ -1637,9 +1637,16 @@ std::vector<int> dist_task_list(int T, int world, int rank, int band) {
   return mine;
 }
 
+// Large systems on few ranks: all-reducing the packed system and running the blocked tcgen05 solve
+// (ba_solve_tc.cuh) on every rank beats the distributed DMMA solve (2,000 cameras on 2 ranks: 9.9 ms
+// + the all-reduce against 15.0 ms); from 4 ranks on the distributed solve wins.
+static bool tc_preferred_over_dist(const Context& c) {
+  return c.tc_min_tiles > 0 && c.ld / NB >= c.tc_min_tiles && c.ld / NB > c.tc_window + 1 && c.comm_world <= c.tc_over_dist_max_world;
+}
+
 bool dist_solve_selected(const Context& c) {
   return c.comm_world > 1 && c.comm_buf && c.dist_off != 0 && c.sys_state == kSysLocal && c.dist_min_tiles > 0 &&
-         c.ld / NB >= c.dist_min_tiles && c.ld / NB < 16384;
+         c.ld / NB >= c.dist_min_tiles && c.ld / NB < 16384 && !tc_preferred_over_dist(c);
 }
 
 static cudaError_t launch_solve_dist(Context& c, bool have_mask, cudaStream_t st) {

@@ -349,7 +349,8 @@ class DeviceProblem(object):
                          ("PYSFM_B200_TC_MIN_TILES", _lib.BA_OPT_TC_MIN_TILES),
                          ("PYSFM_B200_TC_SLICES", _lib.BA_OPT_TC_SLICES),
                          ("PYSFM_B200_TC_WINDOW", _lib.BA_OPT_TC_WINDOW),
-                         ("PYSFM_B200_TC_BK", _lib.BA_OPT_TC_BK)):
+                         ("PYSFM_B200_TC_BK", _lib.BA_OPT_TC_BK),
+                         ("PYSFM_B200_TC_OVER_DIST_MAX_WORLD", _lib.BA_OPT_TC_OVER_DIST_MAX_WORLD)):
             if os.environ.get(env):
                 self.set_option(opt, float(os.environ[env]))
 

@@ -178,6 +178,50 @@ def _dist_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+@_guard
+def _tc_worker(rank, world, port, out_dir):
+    # sharded handles of <= 2 ranks prefer "all-reduce + blocked tcgen05 solve on every rank" over the
+    # distributed solve (BA_OPT_TC_OVER_DIST_MAX_WORLD); thresholds lowered so that 12 tile rows qualify
+    dist = _init(rank, world, port, {"PYSFM_B200_COLLECTIVE": "peer", "PYSFM_B200_DIST_SOLVE_MIN_TILES": "1",
+                                     "PYSFM_B200_TC_MIN_TILES": "4", "PYSFM_B200_TC_WINDOW": "2"})
+    try:
+        from pysfm_b200 import synthetic
+        from pysfm_b200.bundle_adjuster import BundleAdjuster
+        b = synthetic.make_scene(**SCENE_DIST)
+        ba = BundleAdjuster(b, device="cuda:%d" % rank, verbose=False, shard=True)
+        p = ba._problem
+        assert p.peer_comm and not p.dist_solve and p.tc_solve_active()
+        n0 = p.launch_count()
+        motion, structure = ba.compute_update(10.0)
+        launches = p.launch_count() - n0
+        parts = ba._gather_objects(dict(motion=motion))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "tc.npz"), motion=motion, structure=structure, launches=launches,
+                     same_bits=all(np.array_equal(q["motion"], motion) for q in parts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_blocked_tcgen05_solve_on_sharded_handles(tmp_path, cuda_device):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import ba_oracle
+    from pysfm_b200 import synthetic
+    from conftest import relerr
+    _spawn(_tc_worker, 2, (_free_port(), str(tmp_path)))
+    got = np.load(os.path.join(str(tmp_path), "tc.npz"))
+    a = synthetic.make_arrays(**SCENE_DIST)
+    nc, nt = SCENE_DIST["n_cam"], SCENE_DIST["n_pt"]
+    P = ba_oracle.Problem(a["K"], a["Rs"], a["ts"], a["pts"], a["obs_cam"], a["obs_track"], a["obs_uv"],
+                          ('gaussian', np.eye(2)), np.arange(1, nc), np.arange(nt))
+    m2, s2 = ba_oracle.compute_update(P, 10.0)
+    assert relerr(got["motion"], m2) < 1e-7
+    assert relerr(got["structure"], s2) < 1e-7
+    assert bool(got["same_bits"]), "ranks disagree on the bits of dC"
+    assert int(got["launches"]) > 20          # elimination + all-reduce + the windows of the blocked solve + back-substitution
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_distributed_reduced_solve(world, tmp_path, cuda_device):
     import torch

@@ -33,6 +33,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     os.environ["PYSFM_B200_DIST_SOLVE_MIN_TILES"] = "1"
+    os.environ["PYSFM_B200_TC_OVER_DIST_MAX_WORLD"] = "0"   # (2 ranks would otherwise all-reduce and run the blocked tcgen05 solve)
     os.environ["PYSFM_B200_DIST_BAND"] = str(args.band)
     os.environ["PYSFM_B200_SOLVER_PROFILE"] = "1"
     os.environ["PYSFM_B200_STRICT_FLAGS"] = str(args.strict)
