@@ -1753,6 +1753,7 @@ cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0
   g.ntiles = tc::count_tiles(g.n_nb);
   g.dbg_acc = c.tc_dbg; g.dbg_ld = c.tc_dbg ? c.tc_dbg_ld : 0;
   g.dbg_skip = c.tc_dbg_skip;
+  g.wait_limit_ns = (unsigned long long)(c.spin_timeout_ms * 1e6);
   g.dbg_time = c.tc_dbg_time;
   if (g.ntiles <= 0) return cudaSuccess;
   int grid = g.ntiles < c.num_sms ? g.ntiles : c.num_sms;

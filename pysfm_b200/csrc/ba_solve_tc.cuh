@@ -47,7 +47,6 @@ constexpr int kThreads = 320;    // warp 0: TMA producer, warp 1: TMEM owner + M
 constexpr int kEpilogueThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kMaxWindowTiles = 16;
-constexpr unsigned long long kWaitLimitNs = 3000000000ull;   // a barrier that has not moved for 3 s is a bug: give up, report
 
 struct SyrkArgs {
   double* __restrict__ A;             // dense lower, column-major, ld
@@ -62,6 +61,7 @@ struct SyrkArgs {
   int n_nb;      // 64-wide column blocks of the trailing matrix
   int ntiles;
   int stages;
+  unsigned long long wait_limit_ns;   // budget of the launch for waiting on its barriers (BA_OPT_SPIN_TIMEOUT_MS)
   int dbg_ld;    // row pitch of dbg_acc (0 = off)
   int dbg_skip;  // microbenchmarks only: 1 = no TMA loads, 2 = no MMAs, 4 = no epilogue work, 8 = drain without the FP64
                  // combination, 16 = no load / store of A (results are garbage)
@@ -94,12 +94,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: false = the launch is being abandoned (this wait or another one ran out of time).
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* s_abort, unsigned long long t0) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* s_abort, unsigned long long t0,
+                                          unsigned long long limit_ns) {
   unsigned int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 255u) == 0u) {
       if (*s_abort) return false;
-      if (now_ns() - t0 > kWaitLimitNs) {
+      if (now_ns() - t0 > limit_ns) {
         *s_abort = 1;
         return false;
       }
@@ -224,7 +225,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kc = 0; kc < nk && ok; ++kc) {
           {
             TC_T0();
-            ok = mbar_wait(&empty_bar[stage], phase ^ 1u, abortp, t0);
+            ok = mbar_wait(&empty_bar[stage], phase ^ 1u, abortp, t0, g.wait_limit_ns);
             TC_ADD(0);
           }
           if (!ok) break;
@@ -253,7 +254,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
         {   // the epilogue has drained the accumulators of the previous tile
           TC_T0();
-          const bool okt = mbar_wait(&tmem_empty_bar, tphase ^ 1u, abortp, t0);
+          const bool okt = mbar_wait(&tmem_empty_bar, tphase ^ 1u, abortp, t0, g.wait_limit_ns);
           TC_ADD(0);
           if (!okt) break;
         }
@@ -262,7 +263,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kc = 0; kc < nk; ++kc) {
           {
             TC_T0();
-            ok = mbar_wait(&full_bar[stage], phase, abortp, t0);
+            ok = mbar_wait(&full_bar[stage], phase, abortp, t0, g.wait_limit_ns);
             TC_ADD(1);
           }
           if (!ok) break;
@@ -325,7 +326,7 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       bool ok;
       {
         TC_T0();
-        ok = __all_sync(0xffffffffu, mbar_wait(&tmem_full_bar, fphase, abortp, t0));   // (tcgen05.ld is warp-collective)
+        ok = __all_sync(0xffffffffu, mbar_wait(&tmem_full_bar, fphase, abortp, t0, g.wait_limit_ns));   // (tcgen05.ld is warp-collective)
         TC_ADD(0);
       }
       tcgen05_fence_after();
