@@ -1792,10 +1792,10 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
   g.x = c.dC;
   for (int j0 = 0; j0 < T; j0 += w) {
     const int Tw = T - j0;                       // tile rows of the trailing matrix
-    // What is left is one window, or small enough that the dataflow kernel alone is faster on it
-    // (below ~80 tile rows a panel leaves most SMs idle behind the chain and the trailing update has
-    // fewer tiles than SMs): factor it all in this launch.
-    const bool last = Tw <= w + 1 || (j0 > 0 && Tw < c.tc_min_tiles);
+    // What is left is one window: factor it all in this launch.  (Handing the last ~80 tile rows to the
+    // dataflow kernel in one launch, where it beats the blocked path on a system of its own, was
+    // measured and lost 0.13 ms at 11,994^2: inside the solve its panels are already in L2.)
+    const bool last = Tw <= w + 1;
     const int c0 = j0 * NB;
     // tickets of the leading w tile columns: C_0, then per column jc < w the T' - jc tasks D_{jc+1}, C_{jc+1}, (jc+2.., jc)
     const int ntasks = last ? 1 + (Tw - 1) * (Tw + 2) / 2 : 1 + w * Tw - w * (w - 1) / 2;
