@@ -6,6 +6,10 @@
 # torch's pool and go unnoticed -- this is how the prefetch past the last chunk of the tile-streamed
 # back-substitution was found).  racecheck / synccheck cover the shared-memory protocols of the
 # elimination kernel and the solver (named barriers, staging slots, bulk-copy sources).
+# The tcgen05 trailing update / blocked solve have their own harness (memcheck, racecheck and synccheck
+# clean: profiles/r2t_sanitizer.txt):
+#   compute-sanitizer --tool memcheck tools/microbench/tc_bench syrk 704 2 6 64
+#   compute-sanitizer --tool memcheck tools/microbench/tc_bench solve 199 8 6 64 1 1
 set -e
 cd "$(dirname "$0")/.."
 tool="${1:-memcheck}"
