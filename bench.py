@@ -342,6 +342,43 @@ def run_c4(args, dev, world, rank):
     steps = max(3, min(args.steps, 20))
     total_ms, launches, _ = h.timed(steps, 3)
     stage_ms = h.stages(min(steps, 5))
+    # blocked solve (tcgen05 trailing updates): CUDA-event breakdown of the solve stage through the C ABI,
+    # and the INT8 throughput of the trailing updates against the tensor peak
+    tc_block = None
+    if h.prob.tc_solve_active():
+        from pysfm_b200 import _lib
+        h.prob.set_option(_lib.BA_OPT_SOLVER_PROFILE, 1)
+        h.prob.tc_solve_profile(reset=True)
+        for _ in range(3):
+            h.flush.zero_()
+            h.step()
+        prof = h.prob.tc_solve_profile(reset=True)
+        h.prob.set_option(_lib.BA_OPT_SOLVER_PROFILE, 0)
+        w = int(float(os.environ.get("PYSFM_B200_TC_WINDOW", 8)))
+        S = int(float(os.environ.get("PYSFM_B200_TC_SLICES", 6)))
+        T = (h.prob.n_sys + 63) // 64
+        tiles = 0
+        for j0 in range(0, T, w):
+            if T - j0 <= w + 1:
+                break
+            n_nb = T - j0 - w
+            mb = (n_nb + 1) // 2
+            tiles += mb * (mb + 1) - (n_nb & 1)
+        int8_ops = tiles * (S * (S + 1) // 2) * 2.0 * 128 * 64 * (64 * w)
+        ach = int8_ops / (prof["trailing_updates"] * 1e-3) / 1e12 if prof["trailing_updates"] > 0 else 0.0
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops"))
+        except Exception:
+            bf16 = None
+        tc_block = {"solve_breakdown_ms": prof,
+                    "trailing_update_roofline": {
+                        "bound": "tensor", "kernel": "tc::ozaki_syrk_kernel<%d, 64>" % S, "achieved": ach, "unit": "TOP/s (INT8, dense)",
+                        "peak": 4500.0, "frac": ach / 4500.0,
+                        "peak_source": "nominal dense INT8 of B200 (MEASURED_PEAKS.json has no INT8 figure; twice its measured bf16 burst = %s)"
+                                       % ("%.0f" % (2 * bf16) if bf16 else "n/a"),
+                        "frac_of_twice_measured_bf16": (ach / (2 * bf16)) if bf16 else None,
+                        "int8_ops_per_solve": int8_ops, "tiles_128x64": tiles, "slices": S, "window": w,
+                        "timed_by": "CUDA events behind every launch of the solve (ba_tc_solve_profile), 3 solves"}}
     cost, cand, status, dC, dP = h.results()
     out = None
     if rank == 0:
@@ -373,6 +410,8 @@ def run_c4(args, dev, world, rank):
                "fp64_tflops_peak_per_gpu": FP64_PEAK_TFLOPS,
                "final": {"cost": cost, "cand_cost": cand, "solve_status": status},
                "parity": par, "setup_s": setup_s, "oracle_cpu_s_per_step": float(g["seconds"])}
+        if tc_block:
+            out.update(tc_block)
     h.barrier()
     h.ba.close()
     return out

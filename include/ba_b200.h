@@ -293,6 +293,13 @@ int ba_sync(ba_handle h, void* stream);
  * [11] chain tasks, [12] diagonal-update tasks.  Needs BA_OPT_SOLVER_PROFILE = 1.  Synchronises. */
 int ba_solver_profile(ba_handle h, unsigned long long* out16_host, int reset, void* stream);
 
+/* CUDA-event breakdown of the blocked reduced solve (BA_OPT_TC_MIN_TILES) since the last reset, in
+ * milliseconds summed over the solves run with BA_OPT_SOLVER_PROFILE = 1: [0] expand, [1] panels (FP64
+ * dataflow kernel on the leading tile columns), [2] INT8 slices + right-hand side update, [3] trailing
+ * updates on tcgen05, [4] backward substitution; [5] = number of solves.  Synchronises on the last
+ * profiled solve.  Diagnostics (the reference has none; SURVEY section 5: stage timers). */
+int ba_tc_solve_profile(ba_handle h, double* out6_host, int reset);
+
 /* Test entry of the tcgen05 trailing update that the blocked factorisation of large reduced
  * systems (BA_OPT_TC_MIN_TILES) applies after every panel -- one step of the Cholesky behind
  * solve_motion_normal_eqns (bundle_adjuster.py:281-312, numpy.linalg.solve there).  Stateless;

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ba_set_solution": (ctypes.c_int, [_vp, _vp, _vp]),
     "ba_sync": (ctypes.c_int, [_vp, _vp]),
     "ba_solver_profile": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "ba_tc_solve_profile": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
     "ba_launch_count": (ctypes.c_longlong, [_vp]),
     "ba_tc_trailing_update_host": (ctypes.c_int, [ctypes.c_int] * 5 + [_vp] * 6),
 }

@@ -175,6 +175,7 @@ int ba_destroy(ba_handle h) {
                   h->tc_slices, h->tc_scale, h->tc_save};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->tc_ev) cudaEventDestroy(e);
   for (int p = 0; p < ba::kMaxPeers; ++p)
     if (h->comm_peer[p] && p != h->comm_rank) cudaIpcCloseMemHandle(h->comm_peer[p]);
   if (h->rec_scratch) cudaFree(h->rec_scratch);
@@ -585,6 +586,19 @@ int ba_solver_profile(ba_handle h, unsigned long long* out16, int reset, void* s
   BA_CUDA(h, cudaMemcpyAsync(out16, h->solve_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (reset) BA_CUDA(h, cudaMemsetAsync(h->solve_prof, 0, 16 * sizeof(unsigned long long), st));
   BA_CUDA(h, cudaStreamSynchronize(st));
+  return BA_OK;
+}
+
+int ba_tc_solve_profile(ba_handle h, double* out6_host, int reset) {
+  if (!h || !out6_host) return BA_ERR_BAD_ARGUMENT;
+  BA_ON_DEVICE(h);
+  ba::tc_fold_profile(*h);
+  for (int i = 0; i < 5; ++i) out6_host[i] = h->tc_prof_ms[i];
+  out6_host[5] = (double)h->tc_prof_solves;
+  if (reset) {
+    for (int i = 0; i < 5; ++i) h->tc_prof_ms[i] = 0.0;
+    h->tc_prof_solves = 0;
+  }
   return BA_OK;
 }
 

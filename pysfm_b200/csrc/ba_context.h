@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 
 #include "ba_math.cuh"
 
@@ -161,6 +162,13 @@ struct Context {
   unsigned long long* tc_dbg_time = nullptr;  // microbenchmarks: role timers of the trailing-update kernel (SyrkArgs::dbg_time)
   int tc_dbg_skip = 0;                      // microbenchmarks: roles of the trailing-update kernel switched off (SyrkArgs::dbg_skip)
   bool tc_attr_set[16] = {false, false, false, false, false, false, false, false, false, false, false, false, false, false, false, false};
+  // CUDA-event breakdown of the blocked solve (BA_OPT_SOLVER_PROFILE; ba_tc_solve_profile): one event behind every
+  // launch, tagged with what the time since the previous event was spent on
+  std::vector<cudaEvent_t> tc_ev;
+  std::vector<int> tc_ev_cat;
+  int tc_ev_used = 0;
+  double tc_prof_ms[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // expand | panels | slices | trailing updates | backward substitution
+  long long tc_prof_solves = 0;
   int tc_cfg[4] = {0, 0, 0, 0};             // (slices, window, bk, ld) the buffers and tensor maps were built for
   alignas(64) unsigned char tc_map_a[128];  // CUtensorMap: box 128 rows x bk bytes
   alignas(64) unsigned char tc_map_b[128];  // CUtensorMap: box  64 rows x bk bytes
@@ -184,6 +192,7 @@ cudaError_t launch_peer_allreduce_system(Context& c, cudaStream_t st);
 cudaError_t launch_peer_allreduce_costs(Context& c, cudaStream_t st);
 cudaError_t launch_solve(Context& c, bool have_mask, cudaStream_t st);
 bool tc_solve_selected(const Context& c);
+void tc_fold_profile(Context& c);     // folds the pending events of the last profiled blocked solve into tc_prof_ms (synchronises on them)
 cudaError_t tc_prepare(Context& c);   // slice buffers + tensor maps for (c.ld, tc_slices_n, tc_window, tc_bk)
 cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0, const double* saved_rhs, cudaStream_t st);
 bool dist_solve_selected(const Context& c);

@@ -1712,6 +1712,33 @@ bool tc_solve_selected(const Context& c) {
   return c.tc_min_tiles > 0 && c.ld / NB >= c.tc_min_tiles && c.ld / NB > c.tc_window + 1 && !dist_solve_selected(c);
 }
 
+enum { kTcProfExpand = 0, kTcProfPanels = 1, kTcProfSlices = 2, kTcProfUpdates = 3, kTcProfBackward = 4 };
+
+// An event behind the launches issued so far; the time since the previous event is booked on `cat`.
+static void tc_mark(Context& c, int cat, cudaStream_t st) {
+  if (!c.solve_prof_on) return;
+  if (c.tc_ev_used == (int)c.tc_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c.tc_ev.push_back(e);
+    c.tc_ev_cat.push_back(0);
+  }
+  c.tc_ev_cat[c.tc_ev_used] = cat;
+  cudaEventRecord(c.tc_ev[c.tc_ev_used], st);
+  c.tc_ev_used += 1;
+}
+
+void tc_fold_profile(Context& c) {
+  if (c.tc_ev_used > 1 && cudaEventSynchronize(c.tc_ev[c.tc_ev_used - 1]) == cudaSuccess) {
+    for (int i = 1; i < c.tc_ev_used; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c.tc_ev[i - 1], c.tc_ev[i]) == cudaSuccess) c.tc_prof_ms[c.tc_ev_cat[i]] += ms;
+    }
+    c.tc_prof_solves += 1;
+  }
+  c.tc_ev_used = 0;
+}
+
 cudaError_t tc_prepare(Context& c) {
   const int ld = c.ld, w = c.tc_window, K = NB * w, S = c.tc_slices_n;
   if (c.tc_slices && c.tc_cfg[0] == S && c.tc_cfg[1] == w && c.tc_cfg[2] == c.tc_bk && c.tc_cfg[3] == ld) return cudaSuccess;
@@ -1745,6 +1772,7 @@ cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0
   if ((e = tc::launch_slice(c.tc_slices_n, A, ld, c0, K, rhs, saved_rhs, reinterpret_cast<int8_t*>(c.tc_slices), (size_t)ld_pad * K,
                             c.tc_scale, st)) != cudaSuccess) return e;
   c.launches += 1;
+  tc_mark(c, kTcProfSlices, st);
   tc::SyrkArgs g;
   memset(&g, 0, sizeof g);
   g.A = A; g.scale = c.tc_scale; g.status = &c.scalars->status; g.abort = c.solve_abort;
@@ -1761,6 +1789,7 @@ cudaError_t launch_tc_trailing_update(Context& c, double* A, double* rhs, int c0
   e = tc::launch_syrk(c.tc_slices_n, c.tc_bk, *reinterpret_cast<const CUtensorMap*>(c.tc_map_a),
                       *reinterpret_cast<const CUtensorMap*>(c.tc_map_b), g, grid, st, c.tc_attr_set);
   c.launches += 1;
+  tc_mark(c, kTcProfUpdates, st);
   return e;
 }
 
@@ -1771,9 +1800,14 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
   const double* packed = (c.sys_state == kSysReduced && c.comm_buf) ? c.comm_buf + comm_pad(c.sys_len) : c.sys;
   double* const A = c.Adense;
   double* const rhs = c.Adense + (size_t)ld * ld;
+  if (c.solve_prof_on) {
+    tc_fold_profile(c);              // (the previous profiled solve, if nobody asked for it)
+    tc_mark(c, kTcProfExpand, st);   // origin of this solve's time line
+  }
   expand_system_kernel<<<ld, 256, 0, st>>>(packed, c.n_opt_cam, c.n_sys, ld, c.cam_mask, have_mask, A, rhs, c.solve_tickets,
                                            &c.scalars->status, c.dC, c.solve_abort, nullptr, 1.0);
   c.launches += 1;
+  tc_mark(c, kTcProfExpand, st);
   if (!c.solve_attr_set) {
     if ((e = cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSolveSmemBytes)) != cudaSuccess) return e;
@@ -1817,6 +1851,7 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
     chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
     c.launches += 1;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    tc_mark(c, kTcProfPanels, st);
     if (last) break;
     if ((e = launch_tc_trailing_update(c, A, rhs, c0, c.tc_save, st)) != cudaSuccess) return e;
   }
@@ -1834,6 +1869,7 @@ static cudaError_t launch_solve_tc(Context& c, bool have_mask, cudaStream_t st) 
   if (c.solve_grid_cap > 0 && grid > c.solve_grid_cap) grid = c.solve_grid_cap;
   chol_dataflow_kernel<false><<<grid, kSolveThreads, kSolveSmemBytes, st>>>(g);
   c.launches += 2;
+  tc_mark(c, kTcProfBackward, st);
   return cudaGetLastError();
 }
 

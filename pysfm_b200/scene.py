@@ -620,5 +620,17 @@ class DeviceProblem(object):
         """True when ba_solve takes the blocked path with tcgen05 trailing updates (BA_OPT_TC_MIN_TILES)."""
         return bool(self.lib.ba_tc_solve_active(self.h))
 
+    def tc_solve_profile(self, reset=True):
+        """CUDA-event breakdown of the blocked solves run since the last reset with BA_OPT_SOLVER_PROFILE = 1:
+        dict of milliseconds PER SOLVE (expand, panels, slices, trailing_updates, backward) + 'solves'."""
+        import numpy as np
+        out = np.zeros(6)
+        self._chk(self.lib.ba_tc_solve_profile(self.h, ctypes.c_void_p(out.ctypes.data), int(bool(reset))), "ba_tc_solve_profile")
+        n = max(out[5], 1.0)
+        names = ("expand", "panels", "slices", "trailing_updates", "backward")
+        d = dict((k, float(out[i] / n)) for i, k in enumerate(names))
+        d["solves"] = int(out[5])
+        return d
+
     def launch_count(self):
         return int(self.lib.ba_launch_count(self.h))

@@ -124,3 +124,30 @@ def test_config5_steps_through_the_blocked_solve(cuda_device):
         assert relerr(motion, g["sweep_motion"][i]) < 1e-7, lam
         assert relerr(structure[::stride], g["sweep_structure_sample"][i]) < 1e-7, lam
         assert abs(cand - float(g["sweep_cand_cost"][i])) < 1e-8 * float(g["sweep_cand_cost"][i]), lam
+
+
+def test_blocked_solve_event_breakdown(cuda_device):
+    """ba_tc_solve_profile: CUDA-event times of the stages of the blocked solve (stage timers)."""
+    from pysfm_b200 import synthetic, _lib
+    from pysfm_b200.bundle_adjuster import BundleAdjuster
+    nc = 300
+    b = synthetic.make_scene(nc + 1, 40, 4, 31)
+    ba = BundleAdjuster(b, device=cuda_device, verbose=False)
+    p = ba._problem
+    p.set_option(_lib.BA_OPT_TC_MIN_TILES, 1)
+    p.set_option(_lib.BA_OPT_SOLVER_PROFILE, 1)
+    rs = np.random.RandomState(3)
+    n = 6 * nc
+    G = rs.randn(n, n + 5)
+    A = G @ G.T / n + np.eye(n)
+    S = A.reshape(nc, 6, nc, 6).transpose(0, 2, 1, 3).copy()
+    rhs = rs.randn(nc, 6)
+    p.tc_solve_profile(reset=True)
+    x = ba.solve_motion_normal_eqns(S, rhs, np.ones(n, bool))
+    x = ba.solve_motion_normal_eqns(S, rhs, np.ones(n, bool))
+    prof = p.tc_solve_profile(reset=True)
+    assert prof["solves"] == 2
+    for k in ("expand", "panels", "slices", "trailing_updates", "backward"):
+        assert 0.0 < prof[k] < 50.0, (k, prof)
+    assert p.tc_solve_profile()["solves"] == 0
+    assert relerr(x.flatten(), np.linalg.solve(A, rhs.reshape(-1))) < 1e-9
