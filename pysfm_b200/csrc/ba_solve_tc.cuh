@@ -26,9 +26,10 @@
 //                           that lacks this window's terms)
 //   chol_dataflow_kernel    L11, L21 (all rows), L11^-1 tiles, y of the window        [DMMA]
 //   slice_panel_kernel      row scales + S INT8 slice matrices of L21 (K-major, the TMA source) and
-//                           b[rows below] -= L21 y_window                              [FP64, HBM-bound]
+//                           b[rows below] -= L21 y_window                              [FP64, memory]
 //   ozaki_syrk_kernel       A22 -= L21 L21^T, lower triangle, 128 x 64 tiles, persistent,
-//                           warp-specialised: TMA producer / MMA issuer / 4 epilogue warps  [tcgen05]
+//                           warp-specialised: TMA producer / MMA issuer / 8 epilogue warps; up to four
+//                           slice pairs per tcgen05.mma (N = 256)                      [tcgen05]
 //
 // Accuracy (tests/test_ozaki_model.py holds a numpy restatement of this arithmetic to FP64):
 // S = 6 reproduces the FP64 solve of BA reduced systems to ~1e-11 relative at condition 1e4
